@@ -1,0 +1,549 @@
+#!/usr/bin/env python3
+"""bench.py -- buoy-steps/s of the B200 buoy-advection hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5|cfg4|cfg3|cfg2]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+  python bench.py --impl reference ...        the reference's CPU implementation on host cores
+
+A "step" is one hourly record advanced for every buoy of this rank (one launch of
+k_advect_step = the body of si3_part_tracker.py:378-493 incl. the lat/lon update).
+Workloads (BASELINE.json configs), all synthetic with fixed seeds, weak scaling:
+  cfg5 (default)  1/12-degree-class grid 1700x1475, 12.5 M buoys per GPU
+                  (= config 5's per-GPU share: 100 M buoys on 8 GPUs)
+  cfg4            same grid, 1 M buoys per GPU (config 4)
+  cfg3 / cfg2     NANUK4-shaped 566x492 grid, HSS1+scattered (~25 k) / HSS5 (~1 k) buoys
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_ALG = 83.0          # algorithmic bytes per buoy-step: 25 state in + 25 out + 33 row
+D2H_PER_BUOY = 33     # y,x f8 + lat,lon f8 + mask i1
+WORKLOADS = {
+    "cfg5": dict(grid="arctic12", buoys=12_500_000, kind="dense", nrec_res=8,
+                 label="cfg5-share: synthetic 1/12deg-class C-grid 1700x1475, 12.5M buoys/GPU (100M on 8 GPUs)"),
+    "cfg4": dict(grid="arctic12", buoys=1_000_000, kind="dense", nrec_res=8,
+                 label="cfg4: synthetic 1/12deg-class C-grid 1700x1475, 1M buoys/GPU"),
+    "cfg3": dict(grid="nanuk4", buoys=0, kind="hss1+scattered", nrec_res=48,
+                 label="cfg3: NANUK4-shaped 566x492, HSS1 (~25k buoys) + scattered seeding"),
+    "cfg2": dict(grid="nanuk4", buoys=0, kind="hss5", nrec_res=48,
+                 label="cfg2: NANUK4-shaped 566x492, HSS5 (~1k buoys), -F"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML; the same counters as the nvidia-smi line of the recipe)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.02):
+        self.samples, self.reasons, self.stop_flag, self.period = [], 0, False, period
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:          # noqa: BLE001
+            log("clock sampler unavailable:", e)
+        self.t = None
+
+    def _once(self):
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            get = getattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                self.nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.reasons |= int(get(self.h))
+        except Exception:               # noqa: BLE001
+            pass
+
+    def _run(self):
+        while not self.stop_flag:
+            self._once()
+            time.sleep(self.period)
+
+    def start(self):
+        if self.h is not None:
+            self.stop_flag = False
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+
+    def stop(self):
+        if self.t:
+            self.stop_flag = True
+            self.t.join()
+            self._once()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = [n for b, n in self.REASONS.items() if self.reasons & b and n != "gpu_idle"]
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max), "reasons": names,
+                "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:                   # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """dram read+write bytes per launch of k_advect_step from the committed ncu --set full capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return t.get(workload, {}).get("dram_bytes_per_launch")
+    except Exception:                   # noqa: BLE001
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+# workload construction (host numpy; not timed)
+# ---------------------------------------------------------------------------------------------
+def build_workload(name, rank, want_latlon_grid=True, n_dense=None):
+    import synth
+    w = WORKLOADS[name]
+    t0 = time.time()
+    g = synth.make_grid(**synth.GRID_PRESETS[w["grid"]], seed=0, with_latlon=want_latlon_grid)
+    U, V, IC = synth.make_records(g, w["nrec_res"], seed=1)
+    if w["kind"] == "dense":
+        ids, SG, SC = synth.dense_seeds(g, n_dense or w["buoys"], IC[0], seed=3 + rank, with_latlon=False)
+    elif w["kind"] == "hss5":
+        ids, SG, SC = synth.hss_seeds(g, IC[0], khss=5)
+    else:
+        i1, G1, C1 = synth.hss_seeds(g, IC[0], khss=1)
+        i2, G2, C2 = synth.scattered_seeds(g, 1000, seed=2 + rank)
+        ids, SG, SC = np.concatenate([i1, i2 + i1.size]), np.concatenate([G1, G2]), np.concatenate([C1, C2])
+    log("[rank %d] workload %s built in %.1fs: grid %dx%d, %d seeds, %d resident records"
+        % (rank, name, time.time() - t0, g["Nj"], g["Ni"], SC.shape[0], w["nrec_res"]))
+    return g, (U, V, IC), SG, SC
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import sitrack_b200 as sit
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log("WARNING: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (sitrack_b200 has no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    K, W = args.steps, args.warmup
+    wl = WORKLOADS[args.workload]
+    g, (U, V, IC), SG, SC = build_workload(args.workload, rank)
+    Nj, Ni = g["Nj"], g["Ni"]
+    R = U.shape[0]
+    eng = sit.TrackEngine(g["Yf"], g["Xf"], g["Yu"], g["Xu"], g["Yv"], g["Xv"], tmask=g["tmask"], device=local)
+    launches = {"n": 0}
+
+    # -- seeding on the device (k_seed_locate), timed separately ------------------------------
+    eng.set_locate_grid(g["latT"], g["lonT"], g["ResKM"])
+    SC_t = torch.from_numpy(SC).to(dev)
+    if SG is None:                                   # dense clouds: lat/lon from our own inverse projection
+        SG_t = torch.empty_like(SC_t)
+        sit._lib.check(eng.L.st_xy2latlon_dev(SC_t.shape[0], SC_t.data_ptr(), SG_t.data_ptr(), 70.0, -45.0,
+                                              torch.cuda.current_stream().cuda_stream))
+        SG_t[:, 1] = torch.remainder(SG_t[:, 1], 360.0)
+    else:
+        SG_t = torch.from_numpy(SG).to(dev)
+    ic0_t = torch.from_numpy(IC[0]).to(dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    cell_t, near_t, keep_t = eng.seed_locate_dev(SG_t, SC_t, ic0_t)
+    e1.record(); torch.cuda.synchronize()
+    seed_ms = e0.elapsed_time(e1)
+    kp = keep_t.bool()
+    pos0_t, cell0_t = SC_t[kp].contiguous(), cell_t[kp].contiguous()
+    nP = int(pos0_t.shape[0])
+    log("[rank %d] seeding: %d of %d seeds kept, k_seed_locate %.2f ms (%.3g buoys/s)"
+        % (rank, nP, SC_t.shape[0], seed_ms, SC_t.shape[0] / (seed_ms * 1e-3)))
+    del SG_t, near_t, keep_t, cell_t
+
+    # -- records resident in HBM --------------------------------------------------------------
+    eng.record_slots(R)
+    for r in range(R):
+        st = eng.staging(r)
+        st[0], st[1], st[2] = U[r], V[r], IC[r]
+        eng.submit_record(r)
+    torch.cuda.synchronize()
+
+    NB = 2
+    o_yx = [torch.empty((nP, 2), dtype=torch.float64, device=dev) for _ in range(NB)]
+    o_ll = [torch.empty((nP, 2), dtype=torch.float64, device=dev) for _ in range(NB)]
+    o_mk = [torch.empty((nP,), dtype=torch.int8, device=dev) for _ in range(NB)]
+    stream = torch.cuda.Stream(dev)
+
+    def reset():
+        eng.set_buoys_dev(pos0_t, cell0_t, stream=stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_steps(nsteps, nwarm, after_step=None):
+        """-> (ms, alive buoy-steps in the timed part).  after_step(k, buf) may enqueue extra work."""
+        reset()
+        na = torch.zeros((nwarm + nsteps,), dtype=torch.int64, device=dev)
+        for k in range(nwarm):
+            b = k % NB
+            eng.step(k % R, k, o_yx[b], o_ll[b], o_mk[b], na[k:k + 1], stream)
+            if after_step:
+                after_step(k, b)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        for k in range(nwarm, nwarm + nsteps):
+            b = k % NB
+            eng.step(k % R, k, o_yx[b], o_ll[b], o_mk[b], na[k:k + 1], stream)
+            if after_step:
+                after_step(k, b)
+        t1.record(stream)
+        barrier()
+        launches["n"] = nsteps
+        return t0.elapsed_time(t1), int(na[nwarm:].sum().item())
+
+    # -- value: K steps, records and state resident in HBM --------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, bsteps = timed_steps(K, W)
+    sampler.stop()
+    clocks = sampler.summary()
+
+    def reduce_max_sum(ms_, bs_):
+        if world == 1:
+            return ms_, bs_
+        t = torch.tensor([ms_], dtype=torch.float64, device=dev)
+        s = torch.tensor([bs_], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        return float(t.item()), int(s.item())
+
+    ms_max, bsteps_all = reduce_max_sum(ms, bsteps)
+    value = bsteps_all / (ms_max * 1e-3)
+    peak, peak_src = measured_peak()
+    # roofline of the dominant kernel on THIS rank: algorithmic bytes / its mean launch duration.
+    # The K launches run back to back on one stream, so the event span / K is the launch duration.
+    achieved = (bsteps / K) * B_ALG / (ms / K * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_advect_step<1,false>", "achieved": round(achieved, 1), "peak": peak,
+            "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload),
+            "peak_source": peak_src, "alg_bytes_per_buoy_step": B_ALG,
+            "buoy_steps_per_launch": bsteps / K, "us_per_launch": round(ms / K * 1e3, 2)}
+
+    # -- optional: the same loop with the per-record NCCL all-gather of positions ----------------
+    extra = {}
+    if world > 1 and not args.no_allgather:
+        comm = torch.cuda.Stream(dev)
+        gathered = torch.empty((world * nP_max(nP, dist, dev), 2), dtype=torch.float64, device=dev)
+        npad = gathered.shape[0] // world
+        send = [torch.zeros((npad, 2), dtype=torch.float64, device=dev) for _ in range(NB)]
+        evs = [None] * NB
+
+        def ag(k, b):
+            ev = torch.cuda.Event(); ev.record(stream)
+            comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                send[b][:nP].copy_(o_yx[b], non_blocking=True)
+                dist.all_gather_into_tensor(gathered, send[b])
+                evs[b] = torch.cuda.Event(); evs[b].record(comm)
+            nb = (k + 1) % NB
+            if evs[nb] is not None:
+                stream.wait_event(evs[nb])          # the buffer the next step overwrites has been sent
+        Ka = max(4, min(K, 200))
+        ms_a, bs_a = timed_steps(Ka, min(W, 5), after_step=ag)
+        torch.cuda.synchronize()
+        ms_a, bs_a = reduce_max_sum(ms_a, bs_a)
+        extra["allgather"] = {"value": bs_a / (ms_a * 1e-3), "unit": "buoy-steps/s", "steps": Ka,
+                              "bytes_per_rank_per_step": int(npad * 16), "what": "k_advect_step + NCCL "
+                              "all_gather_into_tensor of (y,x) f8 per record on a side stream"}
+
+    # -- e2e: host buffers in, host rows out, every step (pinned memory, 3 streams) ---------------
+    Ke = args.e2e_steps if args.e2e_steps > 0 else max(4, min(K, 40 if nP > 2_000_000 else 200))
+    h_rec = torch.from_numpy(np.stack([U, V, IC], axis=1).astype(np.float32)).pin_memory()   # (R,3,Nj,Ni)
+    h_yx = [torch.empty((nP, 2), dtype=torch.float64).pin_memory() for _ in range(NB)]
+    h_ll = [torch.empty((nP, 2), dtype=torch.float64).pin_memory() for _ in range(NB)]
+    h_mk = [torch.empty((nP,), dtype=torch.int8).pin_memory() for _ in range(NB)]
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    checksum = [0.0]
+
+    def e2e_loop(n, k0):
+        ev_in, ev_st, ev_out = {}, {}, {}
+        for k in range(k0, k0 + n):
+            b = k % 2
+            if k - 2 in ev_st:
+                s_in.wait_event(ev_st[k - 2])                       # device slot b free again
+            eng.upload_record(b, h_rec[k % R], s_in)                # H2D of this step's inputs
+            ev_in[k] = torch.cuda.Event(); ev_in[k].record(s_in)
+            stream.wait_event(ev_in[k])
+            if k - NB in ev_out:
+                stream.wait_event(ev_out[k - NB])                   # device out buffer b drained
+            eng.step(b, k, o_yx[b], o_ll[b], o_mk[b], na_e[k:k + 1], stream)
+            ev_st[k] = torch.cuda.Event(); ev_st[k].record(stream)
+            s_out.wait_event(ev_st[k])
+            if k - NB in ev_out:
+                ev_out[k - NB].synchronize()                        # host row buffer b consumed
+                checksum[0] += float(h_yx[b][0, 0])                 # the host reads the result
+            with torch.cuda.stream(s_out):
+                h_yx[b].copy_(o_yx[b], non_blocking=True)           # D2H of the trajectory row
+                h_ll[b].copy_(o_ll[b], non_blocking=True)
+                h_mk[b].copy_(o_mk[b], non_blocking=True)
+            ev_out[k] = torch.cuda.Event(); ev_out[k].record(s_out)
+        torch.cuda.synchronize()
+
+    reset(); eng.record_slots(max(R, 2))
+    na_e = torch.zeros((Ke + 3,), dtype=torch.int64, device=dev)
+    e2e_loop(min(3, Ke), 0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(Ke, 3)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_bs = float(na_e[3:].sum().item())                           # alive buoys advanced in the timed steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev); s = torch.tensor([e2e_bs], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_bs = float(t.item()), float(s.item())
+    e2e = {"value": e2e_bs / e2e_s, "unit": "buoy-steps/s", "h2d_bytes_per_step": int(3 * Nj * Ni * 4),
+           "d2h_bytes_per_step": int(D2H_PER_BUOY * nP), "steps": Ke, "ms_per_step": round(e2e_s / Ke * 1e3, 3),
+           "what": "per record: pinned host u/v/siconc -> st_upload_record -> st_step -> trajectory row "
+                   "(y,x,lat,lon f8 + mask) copied to pinned host memory and read"}
+
+    # -- CPU baseline on this box's host cores (rank 0, N=1 only) ---------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        pos0 = pos0_t.cpu().numpy(); cell0 = cell0_t.cpu().numpy()
+        cpu = cpu_baseline(g, (U, V, IC), pos0, cell0, args)
+
+    if rank == 0:
+        out = {"metric": "buoy-steps/sec", "value": value, "unit": "buoy-steps/s", "n_gpus": world, "steps": K,
+               "warmup": W, "ms_per_step": round(ms_max / K, 5), "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": wl["label"], "buoys_per_gpu": nP, "grid": [Nj, Ni],
+                          "records_resident": R, "uv_strategy": 1, "rdt_s": 3600,
+                          "l2": "inputs larger than L2: per step %.0f MB of buoy state + trajectory rows stream "
+                                "through, %d resident records (%.0f MB) are cycled; no flush"
+                                % (nP * B_ALG / 1e6, R, R * 3 * Nj * Ni * 4 / 1e6),
+                          "parallelism": "buoys sharded over %d GPU(s), record replicated" % world},
+               "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["n"],
+               "clocks": clocks, "seed_locate": {"buoys_per_s": SC_t.shape[0] / (seed_ms * 1e-3), "ms": round(seed_ms, 3)}}
+        out.update(extra)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def nP_max(nP, dist, dev):
+    import torch
+    t = torch.tensor([nP], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baselines (oracle/ is only ever the thing timed here, never on the product path)
+# ---------------------------------------------------------------------------------------------
+def _py_sample_run(g, recs64, pos, cell, nrec):
+    from oracle import pyport
+    nP = pos.shape[0]
+    cur = pos.copy(); nxt = np.empty_like(cur); m = np.zeros(nP, 'i1')
+    jiT = cell.astype(int).copy(); alive = np.ones(nP, 'i1')
+    first = np.zeros(nP, int); last = np.zeros(nP, int) + 10 ** 9
+    vM = np.zeros((nP, 4, 2)); sin_ = np.zeros(nP, bool)
+    n = 0
+    t0 = time.perf_counter()
+    for k in range(nrec):
+        xU, xV, xIC = recs64[k % len(recs64)]
+        n += pyport.advance(g, xU, xV, xIC, k, cur, nxt, m, jiT, alive, first, last, vM, sin_)
+        cur, nxt = nxt, cur
+    return n, time.perf_counter() - t0
+
+
+def cpu_baseline(g, recs, pos0, cell0, args):
+    """Pure-Python port (the reference's execution model) on 1 core + the C oracle on all cores,
+    both on a bounded random sub-sample of the same workload."""
+    from oracle import corc
+    U, V, IC = recs
+    rng = np.random.default_rng(7)
+    nP = pos0.shape[0]
+    npy = min(nP, args.cpu_sample)
+    sel = np.sort(rng.choice(nP, npy, replace=False))
+    recs64 = [(U[k].astype(np.float64), V[k].astype(np.float64), IC[k].astype(np.float64)) for k in range(U.shape[0])]
+    n, dt = _py_sample_run(g, recs64, pos0[sel], cell0[sel], args.cpu_records)
+    out = {"value": n / dt, "unit": "buoy-steps/s", "cores": 1, "kind": "port",
+           "sample": "oracle/pyport.py (interpreted Python like the reference) on %d random buoys of the workload x %d "
+                     "records, %.1f s" % (npy, args.cpu_records, dt)}
+    nc = min(nP, 200_000)
+    selc = np.sort(rng.choice(nP, nc, replace=False))
+    nrc = 24
+    Uc = np.concatenate([U] * (nrc // U.shape[0] + 1))[:nrc]; Vc = np.concatenate([V] * (nrc // U.shape[0] + 1))[:nrc]
+    Ic = np.concatenate([IC] * (nrc // U.shape[0] + 1))[:nrc]
+    t0 = time.perf_counter()
+    r = corc.track(g, Uc, Vc, Ic, pos0[selc], cell0[selc].astype(np.int64), history=False)
+    dtc = time.perf_counter() - t0
+    out["c_oracle"] = {"value": float(r["mask"][1:].sum()) / dtc, "unit": "buoy-steps/s", "cores": os.cpu_count(),
+                       "sample": "oracle/st_oracle.c (OpenMP over buoys) on %d buoys x %d records incl. lat/lon, %.2f s"
+                                 % (nc, nrc, dtc)}
+    return out
+
+
+def _ref_worker(conn, g, recs64, pos, cell):
+    from oracle import pyport
+    nP = pos.shape[0]
+    cur = pos.copy(); nxt = np.empty_like(cur); m = np.zeros(nP, 'i1')
+    jiT = cell.astype(int).copy(); alive = np.ones(nP, 'i1')
+    first = np.zeros(nP, int); last = np.zeros(nP, int) + 10 ** 9
+    vM = np.zeros((nP, 4, 2)); sin_ = np.zeros(nP, bool)
+    while True:
+        k = conn.recv()
+        if k is None:
+            break
+        xU, xV, xIC = recs64[k % len(recs64)]
+        n = pyport.advance(g, xU, xV, xIC, k, cur, nxt, m, jiT, alive, first, last, vM, sin_)
+        cur, nxt = nxt, cur
+        conn.send(n)
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path (interpreted Python; oracle/pyport.py is its
+    pinned port because /root/reference cannot travel to the GPU box) on all host cores: buoys are
+    independent, so each worker process owns a shard of a bounded sample of the same workload."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    wl = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    per = args.ref_buoys_per_core
+    g, (U, V, IC), SG, SC = build_workload(args.workload, 0, want_latlon_grid=(wl["kind"] != "dense"),
+                                           n_dense=4 * cores * per)
+    g.pop("warp", None)
+    from oracle import corc
+    # host cells of the sample: nearest T-point in the km plane, then the oracle's containing-cell search
+    n = min(SC.shape[0], cores * per)
+    rng = np.random.default_rng(7)
+    sel = np.sort(rng.choice(SC.shape[0], n, replace=False))
+    pos = SC[sel]
+    cell = np.zeros((n, 2), np.int64)
+    ok = np.zeros(n, bool)
+    Yt, Xt = g["Yt"], g["Xt"]
+    for b in range(n):                                             # nearest T in the km plane, then the 5-candidate test
+        d2 = (Yt - pos[b, 0]) ** 2 + (Xt - pos[b, 1]) ** 2 if n <= 4096 and Yt.size <= 400_000 else None
+        if d2 is not None:
+            j, i = np.unravel_index(np.argmin(d2), Yt.shape)
+        else:
+            j, i = _guess_cell(g, pos[b])
+        if 2 <= j <= g["Nj"] - 3 and 2 <= i <= g["Ni"] - 3:
+            ok[b], cell[b, 0], cell[b, 1] = corc.find_containing_cell(pos[b, 0], pos[b, 1], j, i, g["Yf"], g["Xf"])
+    pos, cell = pos[ok], cell[ok]
+    n = pos.shape[0]
+    recs64 = [(U[k].astype(np.float64), V[k].astype(np.float64), IC[k].astype(np.float64)) for k in range(U.shape[0])]
+    ctx = mp.get_context("fork")
+    shards = np.array_split(np.arange(n), cores)
+    procs, conns = [], []
+    for s in shards:
+        a, b = ctx.Pipe()
+        p = ctx.Process(target=_ref_worker, args=(b, g, recs64, pos[s], cell[s]), daemon=True)
+        p.start(); procs.append(p); conns.append(a)
+
+    def step(k):
+        for c in conns:
+            c.send(k)
+        return sum(c.recv() for c in conns)
+    for k in range(W):
+        step(k)
+    t0 = time.perf_counter()
+    done = 0
+    for k in range(W, W + K):
+        done += step(k)
+    dt = time.perf_counter() - t0
+    for c in conns:
+        c.send(None)
+    for p in procs:
+        p.join(timeout=5)
+    value = done / dt
+    sample = ("oracle/pyport.py (pinned port of the reference's interpreted loop) on %d host processes, "
+              "%d buoys of the workload per step (bounded sample), %d steps in %.1f s" % (cores, n, K, dt))
+    out = {"impl": "reference", "metric": "buoy-steps/sec", "value": value, "unit": "buoy-steps/s",
+           "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": round(dt / K * 1e3, 4),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": wl["label"], "grid": [g["Nj"], g["Ni"]], "sample_buoys": n},
+           "cpu_baseline": {"value": value, "unit": "buoy-steps/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "buoy-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def _guess_cell(g, p):
+    """Coarse-to-fine nearest T-point in the km plane (input preparation for the CPU arm only)."""
+    Yt, Xt = g["Yt"], g["Xt"]
+    st = 16
+    sub = (Yt[::st, ::st] - p[0]) ** 2 + (Xt[::st, ::st] - p[1]) ** 2
+    j0, i0 = np.unravel_index(np.argmin(sub), sub.shape)
+    j0, i0 = j0 * st, i0 * st
+    ja, jb = max(j0 - 2 * st, 0), min(j0 + 2 * st + 1, Yt.shape[0])
+    ia, ib = max(i0 - 2 * st, 0), min(i0 + 2 * st + 1, Yt.shape[1])
+    d2 = (Yt[ja:jb, ia:ib] - p[0]) ** 2 + (Xt[ja:jb, ia:ib] - p[1]) ** 2
+    j, i = np.unravel_index(np.argmin(d2), d2.shape)
+    return j + ja, i + ia
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=list(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--no-allgather", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=2000, help="buoys in the Python cpu_baseline sample")
+    ap.add_argument("--cpu-records", type=int, default=100)
+    ap.add_argument("--ref-buoys-per-core", type=int, default=96)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = 100 if args.steps is None else args.steps
+        args.warmup = 3 if args.warmup is None else max(args.warmup, 1)
+        run_reference(args)
+    else:
+        args.steps = 2000 if args.steps is None else args.steps
+        args.warmup = 20 if args.warmup is None else max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,164 @@
+/*
+ * sitrack_b200.h -- C ABI of libsitrack_b200.so: the B200 (sm_100a) buoy-advection
+ * hot path of stephanieleroux/sitrack behind plain pointers and sizes.
+ *
+ * The reference is pure Python and has no FFI of its own; each entry point below
+ * names the reference code it replaces (paths relative to the upstream repo) and
+ * is what a ctypes stub in the reference would bind.
+ *
+ * Conventions
+ *   - 2-D grids are row-major (Nj, Ni); coordinate pairs are [y, x] in km on
+ *     NorthPolarStereo(central_longitude=-45, true_scale_latitude=70), or
+ *     [lat, lon] in degrees; cell indices are {jT, iT} int32 pairs.
+ *   - "host" pointers are ordinary (or pinned) CPU memory; "dev" pointers are
+ *     CUDA device memory on the context's device (e.g. torch tensor data_ptr()).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function returns 0 on success or a negative ST_E* code; the message is
+ *     available from st_last_error().  Nothing here prints or exits (the reference
+ *     prints 'ERROR ...' and calls exit(0); the Python wrappers keep that text).
+ *   - entry points marked ASYNC only enqueue work on `stream`.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     ST_ECUDA.
+ */
+#ifndef SITRACK_B200_H
+#define SITRACK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ST_OK        0
+#define ST_EINVAL   -1      /* bad argument                              */
+#define ST_ECUDA    -2      /* CUDA runtime error / no device            */
+#define ST_ESTATE   -3      /* call order (e.g. step before set_buoys)   */
+#define ST_ENOMEM   -4
+
+#define ST_ABI_VERSION 1
+
+typedef struct st_ctx st_ctx;
+
+int         st_abi_version(void);
+/* Message of the last failure on this context; ctx may be NULL for st_create errors. */
+const char *st_last_error(const st_ctx *ctx);
+
+/* ---- context: static grid resident in HBM -------------------------------------------
+ * Replaces the host arrays the tracker builds once per run:
+ *   xYf,xXf (GetModelGrid, sitrack/ncio.py:22-63), xYv,xXv,xYu,xXu (GetModelUVGrid,
+ *   ncio.py:66-92), imaskt, and the constants iUVstrategy (si3_part_tracker.py:37),
+ *   rdt (:31) and rmin_conc (tracking.py:4).
+ * All array arguments are host pointers, (Nj,Ni) each.                                  */
+int  st_create(st_ctx **out, int device, int Nj, int Ni,
+               const double *Yf, const double *Xf, const double *Yu, const double *Xu,
+               const double *Yv, const double *Xv, const int8_t *tmask,
+               int uv_strategy, double rdt, double rmin_conc);
+void st_destroy(st_ctx *ctx);
+
+/* Polar-stereographic parameters of CartNPSkm2Geo1D (util.py:413: lat0=70, lon0=-45). */
+int  st_set_projection(st_ctx *ctx, double lat_ts_deg, double lon0_deg);
+
+/* ---- seeding: SeedInit (tracking.py:98-178) ------------------------------------------
+ * st_set_locate_grid uploads platT, plonT, pResolKM (host, (Nj,Ni); resKM may be NULL)
+ * and builds the coarse-bin spatial hash on the device.
+ * st_seed_locate runs, per buoy, NearestPoint (locate.py:222-276 with
+ * rd_found_km=2.5, max_itr=10) -> Survive (tracking.py:62-93, siconc ic0) ->
+ * FindContainingCell (locate.py:280-330).  Host in/out:
+ *   SG (nP,2) [lat,lon], SC (nP,2) [y,x]; ic0 (Nj,Ni) f4;
+ *   cell (nP,2) containing cell, nearest (nP,2) nearest T-point or -1,-1 (nullable),
+ *   keep (nP) SeedInit's kmask.  Compaction by `keep` is left to the caller.           */
+int  st_set_locate_grid(st_ctx *ctx, const double *latT, const double *lonT, const double *resKM);
+int  st_seed_locate(st_ctx *ctx, int64_t nP, const double *SG, const double *SC, const float *ic0,
+                    int32_t *cell, int32_t *nearest, int8_t *keep);
+/* Same with device pointers, ASYNC on `stream` (ic0_dev (Nj,Ni) f4 on the device).      */
+int  st_seed_locate_dev(st_ctx *ctx, int64_t nP, const double *SG_dev, const double *SC_dev,
+                        const float *ic0_dev, int32_t *cell_dev, int32_t *nearest_dev, int8_t *keep_dev,
+                        void *stream);
+/* NearestPoint alone (locate.py:222-276; no ji_prv box).  Host in/out.
+ * use_brute != 0 runs the reference's own whole-grid scan on the device instead of
+ * the hash search (cross-check).                                                        */
+int  st_nearest_point(st_ctx *ctx, int64_t n, const double *latlon, double rd_found_km, int max_itr,
+                      int use_brute, int32_t *ji, double *dist_km);
+/* FindContainingCell alone (locate.py:280-330) around given T-points.  Host in/out.    */
+int  st_find_containing_cell(st_ctx *ctx, int64_t n, const double *yx, const int32_t *ji_near,
+                             int32_t *cell, int8_t *found);
+
+/* ---- buoy state (xPosC[jt], vJIt, iAlive; si3_part_tracker.py:324-344) ----------------
+ * pos (nP,2) [y,x] km, cell (nP,2).  rec_first/rec_last (nP) are the per-buoy model
+ * record windows z1stModelRec/zLstModelRec (:264-312); pass NULL for -F runs.  All
+ * buoys start alive.  *_dev variants take device pointers and copy device-to-device.    */
+int  st_set_buoys(st_ctx *ctx, int64_t nP, const double *pos, const int32_t *cell,
+                  const int32_t *rec_first, const int32_t *rec_last);
+int  st_set_buoys_dev(st_ctx *ctx, int64_t nP, const double *pos_dev, const int32_t *cell_dev,
+                      const int32_t *rec_first_dev, const int32_t *rec_last_dev, void *stream);
+int  st_get_state(st_ctx *ctx, double *pos, int32_t *cell, int8_t *alive);          /* host out, syncs */
+int  st_state_device_ptrs(st_ctx *ctx, double **pos_dev, int32_t **cell_dev, int8_t **alive_dev);
+int64_t st_num_buoys(const st_ctx *ctx);
+
+/* ---- hourly records (xUu, xVv, xIC; si3_part_tracker.py:372-374) ----------------------
+ * A slot holds one record as three contiguous (Nj,Ni) f4 planes [u_ice | v_ice |
+ * siconc] on the device plus a pinned host staging buffer of the same layout.
+ * st_submit_record (ASYNC) copies staging -> device on `stream` with one
+ * cudaMemcpyAsync; double-buffer with two slots and a copy stream to overlap the
+ * next record's transfer with the current step.                                          */
+int  st_record_slots(st_ctx *ctx, int nslots);
+int  st_record_host_buffer(st_ctx *ctx, int slot, float **staging);       /* 3*Nj*Ni floats, pinned */
+int  st_record_device_buffer(st_ctx *ctx, int slot, float **dev);         /* 3*Nj*Ni floats         */
+int  st_submit_record(st_ctx *ctx, int slot, void *stream);
+/* ASYNC copy of a whole record [u|v|ic] (3*Nj*Ni f4) from caller-owned host memory
+ * (pinned for a truly asynchronous copy) into the slot's device buffer.               */
+int  st_upload_record(st_ctx *ctx, int slot, const float *host_rec, void *stream);
+
+/* ---- the step: body of the records x buoys loop (si3_part_tracker.py:378-493) ----------
+ * ASYNC.  Advances every alive buoy whose window contains file record `jrec` using
+ * the record in `slot`, updates the state in place and writes trajectory row jt+1:
+ *   out_yx_dev (nP,2) -> xPosC[jt+1], out_latlon_dev (nP,2) -> xPosG[jt+1],
+ *   out_mask_dev (nP) -> xmask[jt+1,:,0]; rows of buoys that did not move get -9999 /
+ *   mask 0 (lat/lon of -9999 is converted like the reference does, :493).
+ *   n_alive_dev: uint64 counter incremented by the number of buoys alive at the START
+ *   of the record (:376); zero it first.  Any output pointer may be NULL.               */
+int  st_step(st_ctx *ctx, int slot, int jrec, double *out_yx_dev, double *out_latlon_dev,
+             int8_t *out_mask_dev, uint64_t *n_alive_dev, void *stream);
+/* nrec consecutive records already on the device at rec_dev (record k at
+ * rec_dev + k*rec_stride floats, each [u|v|ic]); outputs (nrec,nP,..) row k at
+ * k*out_stride elements; n_alive_dev (nrec).  One launch, ASYNC.                        */
+int  st_step_multi(st_ctx *ctx, const float *rec_dev, int64_t rec_stride, int nrec, int jrec0,
+                   double *out_yx_dev, double *out_latlon_dev, int8_t *out_mask_dev,
+                   int64_t out_stride, uint64_t *n_alive_dev, void *stream);
+
+/* Host-buffer form of one loop iteration -- what a reference-side binding calls per
+ * record: copies u,v,ic (host, (Nj,Ni) f4 each) to the device, steps, and returns the
+ * trajectory row in host arrays (any of them NULL to skip).  Synchronous.               */
+int  st_track_record_host(st_ctx *ctx, int jrec, const float *u, const float *v, const float *ic,
+                          double *out_yx, double *out_latlon, int8_t *out_mask, int64_t *n_alive);
+
+/* ---- projections (util.py:394-472 via cartopy NorthPolarStereo) ------------------------ */
+int  st_xy2latlon(int device, int64_t n, const double *yx, double *latlon, double lat_ts, double lon0);
+int  st_latlon2xy(int device, int64_t n, const double *latlon, double *yx, double lat_ts, double lon0);
+int  st_xy2latlon_dev(int64_t n, const double *yx_dev, double *latlon_dev, double lat_ts, double lon0,
+                      void *stream);
+
+/* ---- batched scalar predicates on explicit coordinates (host in/out) -------------------
+ * st_intersect2seg : tracking.py:51-58, A,B,C,D (n,2)            -> out (n) 0/1
+ * st_inside_quad   : locate.py:49-78,  yx (n,2), quads (n,4,2)   -> out (n) 0/1
+ * st_cell_walk     : tracking.py:182-249; ring (n,12,2) = 4 cell vertices (BL,BR,UR,UL)
+ *                    then F[jbl-1,ibl] F[jbr-1,ibr] F[jbr,ibr+1] F[jur,iur+1] F[jul+1,iul]
+ *                    F[jur+1,iur] F[jul,iul-1] F[jbl,ibl-1]; kcross_in NULL => CrossedEdge
+ *                    first, else NewHostCell for the given edge -> kcross (n), knhc (n)
+ * st_survive       : tracking.py:62-93 on gathered stencils tm5 (n,5) i1, ic5 (n,5) f8 or
+ *                    NULL (order [j,i] [j,i+1] [j+1,i] [j,i-1] [j-1,i-1])   -> kill (n)
+ * st_haversine     : util.py:85-103, one point against n grid points       -> km (n)      */
+int  st_intersect2seg(int device, int64_t n, const double *A, const double *B, const double *C,
+                      const double *D, int8_t *out);
+int  st_inside_quad(int device, int64_t n, const double *yx, const double *quads, int8_t *out);
+int  st_cell_walk(int device, int64_t n, const double *p1, const double *p2, const double *ring,
+                  const int32_t *kcross_in, int32_t *kcross, int32_t *knhc);
+int  st_survive(int device, int64_t n, const int32_t *ji, int Nj, int Ni, const int8_t *tm5,
+                const double *ic5, double rmin_conc, int32_t *kill);
+int  st_haversine(int device, int64_t n, double plat, double plon, const double *lat, const double *lon,
+                  double *out_km);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SITRACK_B200_H */

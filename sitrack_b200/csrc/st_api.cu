@@ -1,0 +1,634 @@
+// st_api.cu -- the C ABI of include/sitrack_b200.h: context, HBM residency of the
+// static grid / records / buoy state, and thin launch wrappers.  No arithmetic of
+// the tracking path happens on the host in this file.
+#include "../../include/sitrack_b200.h"
+#include "st_kernels.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+using namespace st;
+
+namespace st {
+cudaError_t launch_seed_locate_opt(const LocateGrid& lg, const AdvectGrid& g, const float* ic0,
+                                   long long nP, const pt* SG, const pt* SC, const SeedOut& o,
+                                   double rd_found_km, int max_itr, int do_survive, int do_cell, cudaStream_t st);
+}
+
+struct st_ctx {
+    int device = 0;
+    int Nj = 0, Ni = 0;
+    AdvectGrid grid{};
+    // owned device memory
+    pt *F = nullptr, *U = nullptr, *V = nullptr;
+    int8_t* tmask = nullptr;
+    double *latT = nullptr, *lonT = nullptr, *resKM = nullptr;
+    int *bin_start = nullptr, *bin_pts = nullptr;
+    LocateGrid lg{};
+    bool has_locate = false;
+    // buoys
+    long long nP = 0, capP = 0;
+    pt* pos = nullptr; int2* cell = nullptr; int8_t* alive = nullptr;
+    int32_t *rec_first = nullptr, *rec_last = nullptr;
+    bool has_window = false;
+    // host-API scratch outputs
+    pt *o_yx = nullptr, *o_ll = nullptr; int8_t* o_mask = nullptr; unsigned long long* o_nalive = nullptr;
+    long long capOut = 0;
+    // record slots
+    std::vector<float*> d_rec, h_rec;
+    cudaStream_t stream = nullptr;
+    std::string err;
+};
+
+static thread_local std::string g_err;
+
+static int fail(st_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg;
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(st_ctx* c, cudaError_t e, const char* what)
+{
+    return fail(c, e == cudaErrorMemoryAllocation ? ST_ENOMEM : ST_ECUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail((c), e_, #call); } while (0)
+
+// WGS84, the globe cartopy gives NorthPolarStereo by default
+static const double kA = 6378137.0, kF = 1.0 / 298.257223563;
+
+static double proj_akm1(double lat_ts_deg, double e)
+{
+    const double HALFPI = 1.5707963267948966;
+    const double phits = fabs(lat_ts_deg) * 0.017453292519943295;
+    if (fabs(phits - HALFPI) < 1e-10) return 2.0 / sqrt(pow(1.0 + e, 1.0 + e) * pow(1.0 - e, 1.0 - e));
+    const double s = sin(phits), es = e * s;
+    const double ts = tan(0.5 * (HALFPI - phits)) / pow((1.0 - es) / (1.0 + es), 0.5 * e);
+    return cos(phits) / ts / sqrt(1.0 - es * es);
+}
+
+static ProjConst make_proj(double lat_ts, double lon0)
+{
+    const double es = kF * (2.0 - kF), e = sqrt(es);
+    const double n = kF / (2.0 - kF), n2 = n * n, n3 = n2 * n, n4 = n3 * n, n5 = n4 * n, n6 = n5 * n;
+    ProjConst p;
+    p.k_t = 1000.0 / (kA * proj_akm1(lat_ts, e));
+    // conformal -> geodetic latitude, series in the third flattening (Karney 2011 / GeographicLib)
+    p.c[0] = 2 * n - 2. / 3 * n2 - 2 * n3 + 116. / 45 * n4 + 26. / 45 * n5 - 2854. / 675 * n6;
+    p.c[1] = 7. / 3 * n2 - 8. / 5 * n3 - 227. / 45 * n4 + 2704. / 315 * n5 + 2323. / 945 * n6;
+    p.c[2] = 56. / 15 * n3 - 136. / 35 * n4 - 1262. / 105 * n5 + 73814. / 2835 * n6;
+    p.c[3] = 4279. / 630 * n4 - 332. / 35 * n5 - 399572. / 14175 * n6;
+    p.c[4] = 4174. / 315 * n5 - 144838. / 6237 * n6;
+    p.c[5] = 601676. / 22275 * n6;
+    p.lon0_rad = lon0 * 0.017453292519943295;
+    return p;
+}
+static ProjFwdConst make_proj_fwd(double lat_ts, double lon0)
+{
+    const double es = kF * (2.0 - kF), e = sqrt(es);
+    ProjFwdConst p;
+    p.a_akm1_km = kA * proj_akm1(lat_ts, e) / 1000.0;
+    p.e = e;
+    p.lon0_rad = lon0 * 0.017453292519943295;
+    return p;
+}
+
+static int use_device(st_ctx* c, int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(c, ST_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                     " (libsitrack_b200 has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(c, ST_EINVAL, "device index out of range");
+    CU(c, cudaSetDevice(device));
+    return ST_OK;
+}
+
+template <class T>
+static cudaError_t upload(T** dst, const T* src, size_t n)
+{
+    cudaError_t e = cudaMalloc((void**)dst, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static cudaError_t upload_pts(pt** dst, const double* Y, const double* X, size_t n)
+{
+    std::vector<pt> tmp(n);
+    for (size_t k = 0; k < n; ++k) { tmp[k].y = Y[k]; tmp[k].x = X[k]; }      // layout marshalling only
+    return upload(dst, tmp.data(), n);
+}
+
+struct Scratch {                       // RAII device scratch for the host-array helpers
+    std::vector<void*> p;
+    ~Scratch() { for (void* q : p) cudaFree(q); }
+    template <class T> cudaError_t up(T** d, const T* h, size_t n)
+    { cudaError_t e = upload(d, h, n); if (e == cudaSuccess) p.push_back(*d); return e; }
+    template <class T> cudaError_t alloc(T** d, size_t n)
+    { cudaError_t e = cudaMalloc((void**)d, n * sizeof(T)); if (e == cudaSuccess) p.push_back(*d); return e; }
+};
+
+extern "C" {
+
+int st_abi_version(void) { return ST_ABI_VERSION; }
+
+const char* st_last_error(const st_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int st_create(st_ctx** out, int device, int Nj, int Ni, const double* Yf, const double* Xf,
+              const double* Yu, const double* Xu, const double* Yv, const double* Xv,
+              const int8_t* tmask, int uv_strategy, double rdt, double rmin_conc)
+{
+    if (!out) return fail(nullptr, ST_EINVAL, "st_create: out is NULL");
+    *out = nullptr;
+    if (Nj < 5 || Ni < 5 || (long long)Nj * Ni > 0x7fffffffLL) return fail(nullptr, ST_EINVAL, "st_create: bad grid shape");
+    if (!Yf || !Xf || !tmask) return fail(nullptr, ST_EINVAL, "st_create: Yf, Xf and tmask are required");
+    if (uv_strategy != 0 && uv_strategy != 1) return fail(nullptr, ST_EINVAL, "st_create: uv_strategy must be 0 or 1");
+    if (uv_strategy == 1 && (!Yu || !Xu || !Yv || !Xv))
+        return fail(nullptr, ST_EINVAL, "st_create: uv_strategy=1 needs the U- and V-point coordinates");
+    int rc = use_device(nullptr, device);
+    if (rc) return rc;
+    st_ctx* c = new st_ctx();
+    c->device = device; c->Nj = Nj; c->Ni = Ni;
+    const size_t n = (size_t)Nj * Ni;
+    cudaError_t e = upload_pts(&c->F, Yf, Xf, n);
+    if (e == cudaSuccess && Yu) e = upload_pts(&c->U, Yu, Xu, n);
+    if (e == cudaSuccess && Yv) e = upload_pts(&c->V, Yv, Xv, n);
+    if (e == cudaSuccess) e = upload(&c->tmask, tmask, n);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { rc = cuda_fail(nullptr, e, "st_create"); st_destroy(c); return rc; }
+    c->grid.Nj = Nj; c->grid.Ni = Ni; c->grid.uv_strategy = uv_strategy; c->grid.rdt = rdt;
+    c->grid.rmin_conc = rmin_conc; c->grid.F = c->F; c->grid.U = c->U; c->grid.V = c->V; c->grid.tmask = c->tmask;
+    c->grid.proj = make_proj(70.0, -45.0);
+    *out = c;
+    return ST_OK;
+}
+
+void st_destroy(st_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->F); cudaFree(c->U); cudaFree(c->V); cudaFree(c->tmask);
+    cudaFree(c->latT); cudaFree(c->lonT); cudaFree(c->resKM); cudaFree(c->bin_start); cudaFree(c->bin_pts);
+    cudaFree(c->pos); cudaFree(c->cell); cudaFree(c->alive); cudaFree(c->rec_first); cudaFree(c->rec_last);
+    cudaFree(c->o_yx); cudaFree(c->o_ll); cudaFree(c->o_mask); cudaFree(c->o_nalive);
+    for (float* p : c->d_rec) cudaFree(p);
+    for (float* p : c->h_rec) cudaFreeHost(p);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int st_set_projection(st_ctx* c, double lat_ts_deg, double lon0_deg)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    c->grid.proj = make_proj(lat_ts_deg, lon0_deg);
+    return ST_OK;
+}
+
+// ---- seeding ---------------------------------------------------------------------------
+int st_set_locate_grid(st_ctx* c, const double* latT, const double* lonT, const double* resKM)
+{
+    if (!c || !latT || !lonT) return fail(c, ST_EINVAL, "st_set_locate_grid: latT/lonT required");
+    CU(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)c->Nj * c->Ni;
+    cudaFree(c->latT); cudaFree(c->lonT); cudaFree(c->resKM); cudaFree(c->bin_start); cudaFree(c->bin_pts);
+    c->latT = c->lonT = c->resKM = nullptr; c->bin_start = c->bin_pts = nullptr; c->has_locate = false;
+    CU(c, upload(&c->latT, latT, n));
+    CU(c, upload(&c->lonT, lonT, n));
+    if (resKM) CU(c, upload(&c->resKM, resKM, n));
+    CU(c, locate_build(c->Nj, c->Ni, c->latT, c->lonT, c->resKM, &c->lg, &c->bin_start, &c->bin_pts, c->stream));
+    c->has_locate = true;
+    return ST_OK;
+}
+
+int st_seed_locate_dev(st_ctx* c, int64_t nP, const double* SG, const double* SC, const float* ic0,
+                       int32_t* cell, int32_t* nearest, int8_t* keep, void* stream)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (!c->has_locate) return fail(c, ST_ESTATE, "st_seed_locate: call st_set_locate_grid first");
+    if (nP < 0 || !SG || !SC || !ic0) return fail(c, ST_EINVAL, "st_seed_locate: SG, SC and ic0 are required");
+    CU(c, cudaSetDevice(c->device));
+    SeedOut o{(int2*)cell, (int2*)nearest, keep, nullptr};
+    CU(c, launch_seed_locate(c->lg, c->grid, ic0, nP, (const pt*)SG, (const pt*)SC, o, 1, 1, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_seed_locate(st_ctx* c, int64_t nP, const double* SG, const double* SC, const float* ic0,
+                   int32_t* cell, int32_t* nearest, int8_t* keep)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (!c->has_locate) return fail(c, ST_ESTATE, "st_seed_locate: call st_set_locate_grid first");
+    if (nP < 0 || !SG || !SC || !ic0 || !cell || !keep) return fail(c, ST_EINVAL, "st_seed_locate: NULL argument");
+    if (nP == 0) return ST_OK;
+    CU(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)c->Nj * c->Ni;
+    double *dSG = nullptr, *dSC = nullptr; float* dic = nullptr; int32_t *dcell = nullptr, *dnear = nullptr; int8_t* dkeep = nullptr;
+    int rc = ST_OK;
+    cudaError_t e = upload(&dSG, SG, (size_t)2 * nP);
+    if (e == cudaSuccess) e = upload(&dSC, SC, (size_t)2 * nP);
+    if (e == cudaSuccess) e = upload(&dic, ic0, n);
+    if (e == cudaSuccess) e = cudaMalloc(&dcell, sizeof(int32_t) * 2 * nP);
+    if (e == cudaSuccess) e = cudaMalloc(&dnear, sizeof(int32_t) * 2 * nP);
+    if (e == cudaSuccess) e = cudaMalloc(&dkeep, (size_t)nP);
+    if (e == cudaSuccess) {
+        rc = st_seed_locate_dev(c, nP, dSG, dSC, dic, dcell, dnear, dkeep, c->stream);
+        if (rc == ST_OK) e = cudaStreamSynchronize(c->stream);
+    }
+    if (e == cudaSuccess && rc == ST_OK) e = cudaMemcpy(cell, dcell, sizeof(int32_t) * 2 * nP, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rc == ST_OK && nearest) e = cudaMemcpy(nearest, dnear, sizeof(int32_t) * 2 * nP, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rc == ST_OK) e = cudaMemcpy(keep, dkeep, (size_t)nP, cudaMemcpyDeviceToHost);
+    cudaFree(dSG); cudaFree(dSC); cudaFree(dic); cudaFree(dcell); cudaFree(dnear); cudaFree(dkeep);
+    if (e != cudaSuccess) return cuda_fail(c, e, "st_seed_locate");
+    return rc;
+}
+
+int st_nearest_point(st_ctx* c, int64_t n, const double* latlon, double rd_found_km, int max_itr,
+                     int use_brute, int32_t* ji, double* dist_km)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (!c->has_locate) return fail(c, ST_ESTATE, "st_nearest_point: call st_set_locate_grid first");
+    if (n < 0 || !latlon || !ji) return fail(c, ST_EINVAL, "st_nearest_point: NULL argument");
+    if (n == 0) return ST_OK;
+    CU(c, cudaSetDevice(c->device));
+    double *dll = nullptr, *dd = nullptr; int32_t* dji = nullptr;
+    cudaError_t e = upload(&dll, latlon, (size_t)2 * n);
+    if (e == cudaSuccess) e = cudaMalloc(&dji, sizeof(int32_t) * 2 * n);
+    if (e == cudaSuccess) e = cudaMalloc(&dd, sizeof(double) * n);
+    if (e == cudaSuccess) {
+        if (use_brute) e = launch_nearest_brute(c->lg, n, (const pt*)dll, (int2*)dji, dd, c->stream);
+        else {
+            SeedOut o{nullptr, (int2*)dji, nullptr, dd};
+            e = launch_seed_locate_opt(c->lg, c->grid, nullptr, n, (const pt*)dll, nullptr, o, rd_found_km, max_itr, 0, 0, c->stream);
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(ji, dji, sizeof(int32_t) * 2 * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && dist_km) e = cudaMemcpy(dist_km, dd, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    cudaFree(dll); cudaFree(dji); cudaFree(dd);
+    if (e != cudaSuccess) return cuda_fail(c, e, "st_nearest_point");
+    return ST_OK;
+}
+
+}  // extern "C" (re-opened below; the kernel of st_find_containing_cell needs C++ linkage)
+
+namespace st {
+__global__ void k_find_cell(const AdvectGrid g, long long n, const pt* __restrict__ yx, const int2* __restrict__ near,
+                            int2* __restrict__ cell, int8_t* __restrict__ found)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int dj[5] = {0, 0, 1, 0, -1}, di[5] = {0, 1, 0, -1, 0};
+    const pt q = yx[p]; const int2 k = near[p];
+    bool in = false; int cj = k.x, ci = k.y;
+    for (int kp = 0; kp < 5 && !in; ++kp) {
+        cj = k.x + dj[kp]; ci = k.y + di[kp];
+        if (cj < 1 || cj >= g.Nj || ci < 1 || ci >= g.Ni) continue;   // (the reference would wrap or raise here)
+        const int c = cj * g.Ni + ci;
+        in = inside_quad(q.y, q.x, ldg_pt(g.F, c - g.Ni - 1), ldg_pt(g.F, c - g.Ni), ldg_pt(g.F, c), ldg_pt(g.F, c - 1));
+    }
+    cell[p] = make_int2(cj, ci); found[p] = in;
+}
+}  // namespace st
+
+extern "C" {
+
+int st_find_containing_cell(st_ctx* c, int64_t n, const double* yx, const int32_t* ji_near, int32_t* cell, int8_t* found)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (n < 0 || !yx || !ji_near || !cell || !found) return fail(c, ST_EINVAL, "st_find_containing_cell: NULL argument");
+    if (n == 0) return ST_OK;
+    CU(c, cudaSetDevice(c->device));
+    double* dyx = nullptr; int32_t *dn = nullptr, *dc = nullptr; int8_t* df = nullptr;
+    cudaError_t e = upload(&dyx, yx, (size_t)2 * n);
+    if (e == cudaSuccess) e = upload(&dn, ji_near, (size_t)2 * n);
+    if (e == cudaSuccess) e = cudaMalloc(&dc, sizeof(int32_t) * 2 * n);
+    if (e == cudaSuccess) e = cudaMalloc(&df, (size_t)n);
+    if (e == cudaSuccess) {
+        k_find_cell<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->grid, n, (const pt*)dyx, (const int2*)dn, (int2*)dc, df);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(cell, dc, sizeof(int32_t) * 2 * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(found, df, (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(dyx); cudaFree(dn); cudaFree(dc); cudaFree(df);
+    if (e != cudaSuccess) return cuda_fail(c, e, "st_find_containing_cell");
+    return ST_OK;
+}
+
+// ---- buoy state ----------------------------------------------------------------------------
+static int reserve_buoys(st_ctx* c, int64_t nP, bool window)
+{
+    if (nP > c->capP) {
+        cudaFree(c->pos); cudaFree(c->cell); cudaFree(c->alive); cudaFree(c->rec_first); cudaFree(c->rec_last);
+        c->pos = nullptr; c->cell = nullptr; c->alive = nullptr; c->rec_first = c->rec_last = nullptr; c->capP = 0;
+        CU(c, cudaMalloc(&c->pos, sizeof(pt) * nP));
+        CU(c, cudaMalloc(&c->cell, sizeof(int2) * nP));
+        CU(c, cudaMalloc(&c->alive, (size_t)nP));
+        c->capP = nP;
+    }
+    if (window && !c->rec_first) {
+        CU(c, cudaMalloc(&c->rec_first, sizeof(int32_t) * c->capP));
+        CU(c, cudaMalloc(&c->rec_last, sizeof(int32_t) * c->capP));
+    }
+    return ST_OK;
+}
+
+static int set_buoys_impl(st_ctx* c, int64_t nP, const double* pos, const int32_t* cell, const int32_t* rf,
+                          const int32_t* rl, cudaMemcpyKind kind, cudaStream_t s)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (nP < 0 || (nP > 0 && (!pos || !cell))) return fail(c, ST_EINVAL, "st_set_buoys: pos and cell are required");
+    if ((rf == nullptr) != (rl == nullptr)) return fail(c, ST_EINVAL, "st_set_buoys: rec_first and rec_last go together");
+    CU(c, cudaSetDevice(c->device));
+    c->nP = 0;
+    if (nP > 0) {
+        int rc = reserve_buoys(c, nP, rf != nullptr);
+        if (rc) return rc;
+        CU(c, cudaMemcpyAsync(c->pos, pos, sizeof(pt) * nP, kind, s));
+        CU(c, cudaMemcpyAsync(c->cell, cell, sizeof(int2) * nP, kind, s));
+        CU(c, cudaMemsetAsync(c->alive, 1, (size_t)nP, s));
+        if (rf) {
+            CU(c, cudaMemcpyAsync(c->rec_first, rf, sizeof(int32_t) * nP, kind, s));
+            CU(c, cudaMemcpyAsync(c->rec_last, rl, sizeof(int32_t) * nP, kind, s));
+        }
+    }
+    c->has_window = rf != nullptr;
+    c->nP = nP;
+    return ST_OK;
+}
+
+int st_set_buoys(st_ctx* c, int64_t nP, const double* pos, const int32_t* cell, const int32_t* rf, const int32_t* rl)
+{
+    int rc = set_buoys_impl(c, nP, pos, cell, rf, rl, cudaMemcpyHostToDevice, c ? c->stream : nullptr);
+    if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return ST_OK;
+}
+
+int st_set_buoys_dev(st_ctx* c, int64_t nP, const double* pos, const int32_t* cell, const int32_t* rf,
+                     const int32_t* rl, void* stream)
+{
+    return set_buoys_impl(c, nP, pos, cell, rf, rl, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+}
+
+int st_get_state(st_ctx* c, double* pos, int32_t* cell, int8_t* alive)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    if (c->nP == 0) return ST_OK;
+    if (pos) CU(c, cudaMemcpy(pos, c->pos, sizeof(pt) * c->nP, cudaMemcpyDeviceToHost));
+    if (cell) CU(c, cudaMemcpy(cell, c->cell, sizeof(int2) * c->nP, cudaMemcpyDeviceToHost));
+    if (alive) CU(c, cudaMemcpy(alive, c->alive, (size_t)c->nP, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_state_device_ptrs(st_ctx* c, double** pos, int32_t** cell, int8_t** alive)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (pos) *pos = (double*)c->pos;
+    if (cell) *cell = (int32_t*)c->cell;
+    if (alive) *alive = c->alive;
+    return ST_OK;
+}
+
+int64_t st_num_buoys(const st_ctx* c) { return c ? c->nP : 0; }
+
+// ---- records -------------------------------------------------------------------------------
+int st_record_slots(st_ctx* c, int nslots)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (nslots < 1 || nslots > 4096) return fail(c, ST_EINVAL, "st_record_slots: 1..4096 slots");
+    CU(c, cudaSetDevice(c->device));
+    const size_t bytes = sizeof(float) * 3 * (size_t)c->Nj * c->Ni;
+    while ((int)c->d_rec.size() < nslots) {
+        float *d = nullptr, *h = nullptr;
+        CU(c, cudaMalloc(&d, bytes));
+        cudaError_t e = cudaMallocHost(&h, bytes);
+        if (e != cudaSuccess) { cudaFree(d); return cuda_fail(c, e, "cudaMallocHost(record staging)"); }
+        c->d_rec.push_back(d); c->h_rec.push_back(h);
+    }
+    return ST_OK;
+}
+
+static int check_slot(st_ctx* c, int slot)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (slot < 0 || slot >= (int)c->d_rec.size()) return fail(c, ST_EINVAL, "record slot out of range (call st_record_slots)");
+    return ST_OK;
+}
+
+int st_record_host_buffer(st_ctx* c, int slot, float** staging)
+{
+    int rc = check_slot(c, slot); if (rc) return rc;
+    *staging = c->h_rec[slot];
+    return ST_OK;
+}
+int st_record_device_buffer(st_ctx* c, int slot, float** dev)
+{
+    int rc = check_slot(c, slot); if (rc) return rc;
+    *dev = c->d_rec[slot];
+    return ST_OK;
+}
+int st_submit_record(st_ctx* c, int slot, void* stream)
+{
+    int rc = check_slot(c, slot); if (rc) return rc;
+    CU(c, cudaSetDevice(c->device));
+    const size_t bytes = sizeof(float) * 3 * (size_t)c->Nj * c->Ni;
+    CU(c, cudaMemcpyAsync(c->d_rec[slot], c->h_rec[slot], bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_upload_record(st_ctx* c, int slot, const float* host_rec, void* stream)
+{
+    int rc = check_slot(c, slot); if (rc) return rc;
+    if (!host_rec) return fail(c, ST_EINVAL, "st_upload_record: host_rec is NULL");
+    CU(c, cudaSetDevice(c->device));
+    const size_t bytes = sizeof(float) * 3 * (size_t)c->Nj * c->Ni;
+    CU(c, cudaMemcpyAsync(c->d_rec[slot], host_rec, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+// ---- the step --------------------------------------------------------------------------------
+static BuoyState state_of(st_ctx* c)
+{
+    BuoyState s;
+    s.nP = c->nP; s.pos = c->pos; s.cell = c->cell; s.alive = c->alive;
+    s.rec_first = c->has_window ? c->rec_first : nullptr;
+    s.rec_last = c->has_window ? c->rec_last : nullptr;
+    return s;
+}
+
+int st_step(st_ctx* c, int slot, int jrec, double* out_yx, double* out_latlon, int8_t* out_mask,
+            uint64_t* n_alive, void* stream)
+{
+    int rc = check_slot(c, slot); if (rc) return rc;
+    CU(c, cudaSetDevice(c->device));
+    const size_t npt = (size_t)c->Nj * c->Ni;
+    const float* r = c->d_rec[slot];
+    StepOut o{(pt*)out_yx, (pt*)out_latlon, out_mask, (unsigned long long*)n_alive};
+    CU(c, launch_advect_step(c->grid, r, r + npt, r + 2 * npt, state_of(c), jrec, o, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_step_multi(st_ctx* c, const float* rec_dev, int64_t rec_stride, int nrec, int jrec0, double* out_yx,
+                  double* out_latlon, int8_t* out_mask, int64_t out_stride, uint64_t* n_alive, void* stream)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    const long long npt = (long long)c->Nj * c->Ni;
+    if (!rec_dev || nrec < 0 || rec_stride < 3 * npt) return fail(c, ST_EINVAL, "st_step_multi: bad record stack");
+    if (out_stride < c->nP) return fail(c, ST_EINVAL, "st_step_multi: out_stride < nP");
+    CU(c, cudaSetDevice(c->device));
+    StepOut o{(pt*)out_yx, (pt*)out_latlon, out_mask, (unsigned long long*)n_alive};
+    CU(c, launch_advect_multi(c->grid, rec_dev, rec_stride, nrec, state_of(c), jrec0, o, out_stride, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_track_record_host(st_ctx* c, int jrec, const float* u, const float* v, const float* ic, double* out_yx,
+                         double* out_latlon, int8_t* out_mask, int64_t* n_alive)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (!u || !v || !ic) return fail(c, ST_EINVAL, "st_track_record_host: u, v, ic are required");
+    CU(c, cudaSetDevice(c->device));
+    if (c->d_rec.empty()) { int rc = st_record_slots(c, 1); if (rc) return rc; }
+    const size_t npt = (size_t)c->Nj * c->Ni;
+    cudaStream_t s = c->stream;
+    float* d = c->d_rec[0];
+    if (v == u + npt && ic == u + 2 * npt) {
+        CU(c, cudaMemcpyAsync(d, u, sizeof(float) * 3 * npt, cudaMemcpyHostToDevice, s));
+    } else {
+        CU(c, cudaMemcpyAsync(d, u, sizeof(float) * npt, cudaMemcpyHostToDevice, s));
+        CU(c, cudaMemcpyAsync(d + npt, v, sizeof(float) * npt, cudaMemcpyHostToDevice, s));
+        CU(c, cudaMemcpyAsync(d + 2 * npt, ic, sizeof(float) * npt, cudaMemcpyHostToDevice, s));
+    }
+    if (c->nP > c->capOut) {
+        cudaFree(c->o_yx); cudaFree(c->o_ll); cudaFree(c->o_mask);
+        c->o_yx = c->o_ll = nullptr; c->o_mask = nullptr; c->capOut = 0;
+        CU(c, cudaMalloc(&c->o_yx, sizeof(pt) * c->nP));
+        CU(c, cudaMalloc(&c->o_ll, sizeof(pt) * c->nP));
+        CU(c, cudaMalloc(&c->o_mask, (size_t)c->nP));
+        c->capOut = c->nP;
+    }
+    if (!c->o_nalive) CU(c, cudaMalloc(&c->o_nalive, sizeof(unsigned long long)));
+    if (n_alive) CU(c, cudaMemsetAsync(c->o_nalive, 0, sizeof(unsigned long long), s));
+    StepOut o{out_yx ? c->o_yx : nullptr, out_latlon ? c->o_ll : nullptr, out_mask ? c->o_mask : nullptr,
+              n_alive ? c->o_nalive : nullptr};
+    CU(c, launch_advect_step(c->grid, d, d + npt, d + 2 * npt, state_of(c), jrec, o, s));
+    if (c->nP > 0) {
+        if (out_yx) CU(c, cudaMemcpyAsync(out_yx, c->o_yx, sizeof(pt) * c->nP, cudaMemcpyDeviceToHost, s));
+        if (out_latlon) CU(c, cudaMemcpyAsync(out_latlon, c->o_ll, sizeof(pt) * c->nP, cudaMemcpyDeviceToHost, s));
+        if (out_mask) CU(c, cudaMemcpyAsync(out_mask, c->o_mask, (size_t)c->nP, cudaMemcpyDeviceToHost, s));
+    }
+    unsigned long long na = 0;
+    if (n_alive) CU(c, cudaMemcpyAsync(&na, c->o_nalive, sizeof(na), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    if (n_alive) *n_alive = (int64_t)na;
+    return ST_OK;
+}
+
+// ---- projections and batched predicates (host in/out) -------------------------------------------
+#define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(nullptr, e_, #call); } while (0)
+
+int st_xy2latlon_dev(int64_t n, const double* yx, double* latlon, double lat_ts, double lon0, void* stream)
+{
+    if (n < 0 || !yx || !latlon) return fail(nullptr, ST_EINVAL, "st_xy2latlon_dev: NULL argument");
+    CUS(launch_xy2latlon((const pt*)yx, (pt*)latlon, n, make_proj(lat_ts, lon0), (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_xy2latlon(int device, int64_t n, const double* yx, double* latlon, double lat_ts, double lon0)
+{
+    if (n < 0 || !yx || !latlon) return fail(nullptr, ST_EINVAL, "st_xy2latlon: NULL argument");
+    int rc = use_device(nullptr, device); if (rc) return rc;
+    if (n == 0) return ST_OK;
+    Scratch s; double *a, *b;
+    CUS(s.up(&a, yx, (size_t)2 * n)); CUS(s.alloc(&b, (size_t)2 * n));
+    CUS(launch_xy2latlon((const pt*)a, (pt*)b, n, make_proj(lat_ts, lon0), 0));
+    CUS(cudaMemcpy(latlon, b, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_latlon2xy(int device, int64_t n, const double* latlon, double* yx, double lat_ts, double lon0)
+{
+    if (n < 0 || !yx || !latlon) return fail(nullptr, ST_EINVAL, "st_latlon2xy: NULL argument");
+    int rc = use_device(nullptr, device); if (rc) return rc;
+    if (n == 0) return ST_OK;
+    Scratch s; double *a, *b;
+    CUS(s.up(&a, latlon, (size_t)2 * n)); CUS(s.alloc(&b, (size_t)2 * n));
+    CUS(launch_latlon2xy((const pt*)a, (pt*)b, n, make_proj_fwd(lat_ts, lon0), 0));
+    CUS(cudaMemcpy(yx, b, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_intersect2seg(int device, int64_t n, const double* A, const double* B, const double* C, const double* D, int8_t* out)
+{
+    if (n < 0 || !A || !B || !C || !D || !out) return fail(nullptr, ST_EINVAL, "st_intersect2seg: NULL argument");
+    int rc = use_device(nullptr, device); if (rc) return rc;
+    if (n == 0) return ST_OK;
+    Scratch s; double *a, *b, *c, *d; int8_t* o;
+    CUS(s.up(&a, A, (size_t)2 * n)); CUS(s.up(&b, B, (size_t)2 * n)); CUS(s.up(&c, C, (size_t)2 * n)); CUS(s.up(&d, D, (size_t)2 * n));
+    CUS(s.alloc(&o, (size_t)n));
+    CUS(launch_geom_intersect(n, (pt*)a, (pt*)b, (pt*)c, (pt*)d, o, 0));
+    CUS(cudaMemcpy(out, o, (size_t)n, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_inside_quad(int device, int64_t n, const double* yx, const double* quads, int8_t* out)
+{
+    if (n < 0 || !yx || !quads || !out) return fail(nullptr, ST_EINVAL, "st_inside_quad: NULL argument");
+    int rc = use_device(nullptr, device); if (rc) return rc;
+    if (n == 0) return ST_OK;
+    Scratch s; double *a, *q; int8_t* o;
+    CUS(s.up(&a, yx, (size_t)2 * n)); CUS(s.up(&q, quads, (size_t)8 * n)); CUS(s.alloc(&o, (size_t)n));
+    CUS(launch_geom_inside(n, (pt*)a, (pt*)q, o, 0));
+    CUS(cudaMemcpy(out, o, (size_t)n, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_cell_walk(int device, int64_t n, const double* p1, const double* p2, const double* ring,
+                 const int32_t* kcross_in, int32_t* kcross, int32_t* knhc)
+{
+    if (n < 0 || !p1 || !p2 || !ring) return fail(nullptr, ST_EINVAL, "st_cell_walk: NULL argument");
+    int rc = use_device(nullptr, device); if (rc) return rc;
+    if (n == 0) return ST_OK;
+    Scratch s; double *a, *b, *r; int32_t *ki = nullptr, *kc, *kn;
+    CUS(s.up(&a, p1, (size_t)2 * n)); CUS(s.up(&b, p2, (size_t)2 * n)); CUS(s.up(&r, ring, (size_t)24 * n));
+    if (kcross_in) CUS(s.up(&ki, kcross_in, (size_t)n));
+    CUS(s.alloc(&kc, (size_t)n)); CUS(s.alloc(&kn, (size_t)n));
+    CUS(launch_geom_walk(n, (pt*)a, (pt*)b, (pt*)r, ki, kc, kn, 0));
+    if (kcross) CUS(cudaMemcpy(kcross, kc, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    if (knhc) CUS(cudaMemcpy(knhc, kn, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_survive(int device, int64_t n, const int32_t* ji, int Nj, int Ni, const int8_t* tm5, const double* ic5,
+               double rmin_conc, int32_t* kill)
+{
+    if (n < 0 || !ji || !tm5 || !kill) return fail(nullptr, ST_EINVAL, "st_survive: NULL argument");
+    int rc = use_device(nullptr, device); if (rc) return rc;
+    if (n == 0) return ST_OK;
+    Scratch s; int32_t *a, *o; int8_t* t; double* c = nullptr;
+    CUS(s.up(&a, ji, (size_t)2 * n)); CUS(s.up(&t, tm5, (size_t)5 * n));
+    if (ic5) CUS(s.up(&c, ic5, (size_t)5 * n));
+    CUS(s.alloc(&o, (size_t)n));
+    CUS(launch_geom_survive(n, a, Nj, Ni, t, c, rmin_conc, o, 0));
+    CUS(cudaMemcpy(kill, o, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_haversine(int device, int64_t n, double plat, double plon, const double* lat, const double* lon, double* out_km)
+{
+    if (n < 0 || !lat || !lon || !out_km) return fail(nullptr, ST_EINVAL, "st_haversine: NULL argument");
+    int rc = use_device(nullptr, device); if (rc) return rc;
+    if (n == 0) return ST_OK;
+    Scratch s; double *a, *b, *o;
+    CUS(s.up(&a, lat, (size_t)n)); CUS(s.up(&b, lon, (size_t)n)); CUS(s.alloc(&o, (size_t)n));
+    CUS(launch_haversine(n, plat, plon, a, b, o, 0));
+    CUS(cudaMemcpy(out_km, o, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+}  // extern "C"

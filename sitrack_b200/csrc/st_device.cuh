@@ -1,0 +1,177 @@
+// st_device.cuh -- device-side geometry and projection primitives of the
+// buoy-advection hot path (sm_100a).  One source of truth for every kernel.
+//
+// Parity rule: every quantity the reference computes with Python floats is
+// rebuilt here from the SAME IEEE-754 double operations in the SAME order,
+// spelled with __dadd_rn/__dsub_rn/__dmul_rn/__ddiv_rn so that ptxas can never
+// contract a*b+c into an FMA (Python cannot), whatever -fmad says.  Reference
+// lines are cited per function (paths relative to stephanieleroux/sitrack).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace st {
+
+#define ST_FILL (-9999.0)                 // sitrack/ncio.py:19 FillValue
+
+// A point of the km plane, stored [y, x] like every coordinate pair upstream.
+struct __align__(16) pt { double y, x; };
+
+__device__ __forceinline__ pt ldg_pt(const pt* __restrict__ a, int idx)
+{
+    const double2 v = __ldg(reinterpret_cast<const double2*>(a) + idx);
+    pt r; r.y = v.x; r.x = v.y; return r;
+}
+// streaming (touch-once) accesses: keep them out of the way of the resident
+// geometry / velocity record in L1 and L2
+__device__ __forceinline__ pt ld_stream_pt(const pt* a)
+{
+    const double2 v = __ldcs(reinterpret_cast<const double2*>(a));
+    pt r; r.y = v.x; r.x = v.y; return r;
+}
+__device__ __forceinline__ void st_stream_pt(pt* a, pt v)
+{
+    __stcs(reinterpret_cast<double2*>(a), make_double2(v.y, v.x));
+}
+
+// ---- tracking.py:44-49  _ccw_(A,B,C) = (Cy-Ay)*(Bx-Ax) > (By-Ay)*(Cx-Ax) ----
+__device__ __forceinline__ bool ccw(pt A, pt B, pt C)
+{
+    return __dmul_rn(__dsub_rn(C.y, A.y), __dsub_rn(B.x, A.x)) >
+           __dmul_rn(__dsub_rn(B.y, A.y), __dsub_rn(C.x, A.x));
+}
+
+// ---- tracking.py:51-58  intersect2Seg ---------------------------------------
+// Branch-free: all four orientation tests are evaluated (no side effects, so
+// Python's short-circuit `and` gives the same truth value).
+__device__ __forceinline__ bool intersect2seg(pt A, pt B, pt C, pt D)
+{
+    return (ccw(A, C, D) != ccw(B, C, D)) & (ccw(A, B, C) != ccw(A, B, D));
+}
+
+// ---- locate.py:66-74  one edge (p1->p2) of the ray-casting parity test -------
+__device__ __forceinline__ bool edge_toggles(double y, double x, pt p1, pt p2)
+{
+    const double ymin = (p2.y < p1.y) ? p2.y : p1.y;       // Python min(z1y,z2y)
+    const double ymax = (p2.y > p1.y) ? p2.y : p1.y;
+    const double xmax = (p2.x > p1.x) ? p2.x : p1.x;
+    bool t = false;
+    if (y > ymin && y <= ymax && x <= xmax) {
+        // y>ymin && y<=ymax implies p1.y != p2.y, so xints is always refreshed here
+        const double xints = __dadd_rn(
+            __ddiv_rn(__dmul_rn(__dsub_rn(y, p1.y), __dsub_rn(p2.x, p1.x)), __dsub_rn(p2.y, p1.y)), p1.x);
+        t = (p1.x == p2.x) || (x <= xints);
+    }
+    return t;
+}
+
+// ---- locate.py:49-78  IsInsideQuadrangle ------------------------------------
+// The upstream loop runs 5 passes; pass 0 pairs vertex 0 with itself and can
+// never toggle, leaving the four edges q0q1, q1q2, q2q3, q3q0.
+__device__ __forceinline__ bool inside_quad(double y, double x, pt q0, pt q1, pt q2, pt q3)
+{
+    return edge_toggles(y, x, q0, q1) ^ edge_toggles(y, x, q1, q2) ^
+           edge_toggles(y, x, q2, q3) ^ edge_toggles(y, x, q3, q0);
+}
+
+// ---- tracking.py:182-200  CrossedEdge -> 1 bottom, 2 right, 3 top, 4 left ----
+// (4 is also the fall-through answer when no edge is met.)
+__device__ __forceinline__ int crossed_edge(pt P1, pt P2, pt bl, pt br, pt ur, pt ul)
+{
+    if (intersect2seg(P1, P2, bl, br)) return 1;
+    if (intersect2seg(P1, P2, br, ur)) return 2;
+    if (intersect2seg(P1, P2, ur, ul)) return 3;
+    return 4;
+}
+
+// ---- tracking.py:253-305  UpdtInd4NewCell as (dj,di) ---------------------------
+__device__ __forceinline__ void cell_shift(int knhc, int& jT, int& iT)
+{
+    // 1 down, 2 right, 3 up, 4 left, 5 down-left, 6 down-right, 7 up-right, 8 up-left
+    const int dj = (int)(knhc == 3 || knhc == 7 || knhc == 8) - (int)(knhc == 1 || knhc == 5 || knhc == 6);
+    const int di = (int)(knhc == 2 || knhc == 6 || knhc == 7) - (int)(knhc == 4 || knhc == 5 || knhc == 8);
+    jT += dj; iT += di;
+}
+
+// ---- tracking.py:62-93  Survive (first failing test wins; any >0 kills) -------
+// tmask i1, ic = the CURRENT record's siconc (f4 widened exactly to f8, as the
+// reference's f8 work array holds it, si3_part_tracker.py:372).
+__device__ __forceinline__ bool killed(int jT, int iT, int Nj, int Ni,
+                                       const int8_t* __restrict__ tmask, const float* __restrict__ ic,
+                                       double rmin_conc)
+{
+    if (jT <= 1 || jT >= Nj - 2 || iT <= 1 || iT >= Ni - 2) return true;
+    const int c = jT * Ni + iT;
+    const int zmt = __ldg(tmask + c) + __ldg(tmask + c + 1) + __ldg(tmask + c + Ni) +
+                    __ldg(tmask + c - 1) + __ldg(tmask + c - Ni - 1);          // sic: [jT-1,iT-1]
+    if (zmt < 5) return true;
+    double s = __dadd_rn((double)__ldg(ic + c), (double)__ldg(ic + c + 1));
+    s = __dadd_rn(s, (double)__ldg(ic + c + Ni));
+    s = __dadd_rn(s, (double)__ldg(ic + c - 1));
+    s = __dadd_rn(s, (double)__ldg(ic + c - Ni - 1));
+    return __dmul_rn(0.2, s) < rmin_conc;
+}
+
+// ---- polar stereographic inverse (replaces util.py:413-429 -> cartopy/PROJ) ---
+// PROJ iterates phi = pi/2 - 2 atan(t ((1-e sin phi)/(1+e sin phi))^(e/2)) to
+// 1e-10 rad; here the same conformal->geodetic map is the 6-term series in the
+// third flattening n (|truncation| < 1e-17 rad for WGS84), evaluated by Clenshaw
+// with sin/cos of 2*chi obtained algebraically from t: one atan and one atan2
+// per point instead of ~25 transcendentals.  Not bit-comparable with PROJ by
+// construction (PROJ itself stops at 1e-10); tolerance in tests: 1e-9 degrees.
+struct ProjConst {
+    double k_t;        // 1000 / (a * akm1): km radius -> t = tan(pi/4 - chi/2)
+    double c[6];       // series coefficients of sin(2k chi), k = 1..6
+    double lon0_rad;   // central longitude
+};
+
+__device__ __forceinline__ pt inv_stere(pt yx, const ProjConst& pc)
+{
+    const double HALFPI = 1.5707963267948966, PI = 3.141592653589793, R2D = 57.29577951308232;
+    const double t = sqrt(fma(yx.x, yx.x, yx.y * yx.y)) * pc.k_t;
+    const double t2 = t * t;
+    const double inv = 1.0 / (1.0 + t2);
+    const double s = (1.0 - t2) * inv;              // sin(chi)
+    const double c = 2.0 * t * inv;                 // cos(chi)
+    const double s2 = 2.0 * s * c;                  // sin(2 chi)
+    const double c2x2 = 2.0 * fma(-2.0 * s, s, 1.0);  // 2 cos(2 chi)
+    double b2 = 0.0, b1 = pc.c[5];
+#pragma unroll
+    for (int k = 4; k >= 0; --k) { const double b0 = fma(c2x2, b1, pc.c[k] - b2); b2 = b1; b1 = b0; }
+    const double phi = (HALFPI - 2.0 * atan(t)) + b1 * s2;
+    double lam = (yx.x == 0.0 && yx.y == 0.0) ? 0.0 : atan2(yx.x, -yx.y);
+    lam += pc.lon0_rad;
+    if (lam > PI) lam -= 2.0 * PI;
+    if (lam < -PI) lam += 2.0 * PI;
+    pt r; r.y = phi * R2D; r.x = lam * R2D; return r;     // [lat, lon] degrees
+}
+
+// forward, for the grid-preparation helpers (ncio.py:50-53,86-89)
+struct ProjFwdConst { double a_akm1_km; double e; double lon0_rad; };
+__device__ __forceinline__ pt fwd_stere(pt latlon, const ProjFwdConst& pc)
+{
+    const double D2R = 0.017453292519943295, HALFPI = 1.5707963267948966;
+    const double phi = latlon.y * D2R;
+    const double lam = latlon.x * D2R - pc.lon0_rad;
+    double sphi, cphi; sincos(phi, &sphi, &cphi);
+    const double es = pc.e * sphi;
+    // t = tan(pi/4 - phi/2) / ((1-es)/(1+es))^(e/2); tan(pi/4-phi/2) = cos(phi)/(1+sin(phi))
+    const double t = (fabs(phi - HALFPI) < 1e-15) ? 0.0
+                   : (cphi / (1.0 + sphi)) * exp(pc.e * atanh(es));   // ((1+es)/(1-es))^(e/2) = exp(e atanh(es))
+    const double rho = pc.a_akm1_km * t;
+    double sl, cl; sincos(lam, &sl, &cl);
+    pt r; r.y = -rho * cl; r.x = rho * sl; return r;
+}
+
+// ---- util.py:85-103  Haversine distance [km], same expression order ------------
+__device__ __forceinline__ double haversine_km(double plat, double plon, double xlat, double xlon)
+{
+    const double to_rad = 3.141592653589793 / 180.;
+    const double a1 = sin(__dmul_rn(0.5, __dmul_rn(__dsub_rn(xlat, plat), to_rad)));
+    const double a2 = sin(__dmul_rn(0.5, __dmul_rn(__dsub_rn(xlon, plon), to_rad)));
+    const double a3 = __dmul_rn(cos(__dmul_rn(xlat, to_rad)), cos(__dmul_rn(plat, to_rad)));
+    const double h = __dadd_rn(__dmul_rn(a1, a1), __dmul_rn(__dmul_rn(a3, a2), a2));
+    return __dmul_rn(2. * 6360., asin(sqrt(h)));
+}
+
+}  // namespace st

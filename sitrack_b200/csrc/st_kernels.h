@@ -1,0 +1,90 @@
+// st_kernels.h -- kernel parameter blocks and launchers shared by the .cu files.
+#pragma once
+#include "st_device.cuh"
+
+namespace st {
+
+constexpr int ST_BLOCK = 256;
+
+// Static grid + run constants, passed by value (lives in the kernel's constant bank).
+struct AdvectGrid {
+    int Nj, Ni;
+    int uv_strategy;            // si3_part_tracker.py:37 iUVstrategy
+    double rdt;                 // si3_part_tracker.py:31
+    double rmin_conc;           // tracking.py:4
+    const pt* F;                // (Nj*Ni) [y,x] km, F-points (cell corners)
+    const pt* U;                // U-points (east faces)
+    const pt* V;                // V-points (north faces)
+    const int8_t* tmask;        // (Nj*Ni)
+    ProjConst proj;
+};
+
+// Buoy state, struct of arrays in HBM.
+struct BuoyState {
+    long long nP;
+    pt* pos;                    // [y,x] km
+    int2* cell;                 // {jT, iT}: T-point at the centre of the host cell
+    int8_t* alive;              // 1 alive, 0 discontinued
+    const int32_t* rec_first;   // optional per-buoy record window (no -F); nullptr with -F
+    const int32_t* rec_last;
+};
+
+// One trajectory row (all nullable).
+struct StepOut {
+    pt* yx;                     // (nP) [y,x] km     -> xPosC[jt+1]
+    pt* latlon;                 // (nP) [lat,lon]    -> xPosG[jt+1]
+    int8_t* mask;               // (nP)              -> xmask[jt+1,:,0]
+    unsigned long long* n_alive;
+};
+
+cudaError_t launch_advect_step(const AdvectGrid& g, const float* u, const float* v, const float* ic,
+                               const BuoyState& s, int jrec, const StepOut& o, cudaStream_t st);
+cudaError_t launch_advect_multi(const AdvectGrid& g, const float* rec0, long long rec_stride, int nrec,
+                                const BuoyState& s, int jrec0, const StepOut& o, long long out_stride,
+                                cudaStream_t st);
+cudaError_t launch_xy2latlon(const pt* yx, pt* latlon, long long n, const ProjConst& pc, cudaStream_t st);
+cudaError_t launch_latlon2xy(const pt* latlon, pt* yx, long long n, const ProjFwdConst& pc, cudaStream_t st);
+
+// ---- locate (st_locate.cu) ---------------------------------------------------------
+// Coarse-bin spatial hash of the T-points in a unit-sphere polar stereographic plane.
+struct LocateGrid {
+    int Nj, Ni;
+    const double* latT;         // (Nj*Ni) degrees
+    const double* lonT;
+    const double* resKM;        // (Nj*Ni) local resolution [km] (ncio.py:56-57)
+    // hash
+    int nbx, nby;               // bins along x / y
+    double x0, y0, inv_bin, bin;   // plane origin, 1/bin size, bin size
+    double q2max;               // max |Q|^2 over grid points (plane radius^2)
+    double res_max;             // max resKM
+    const int* bin_start;       // (nbx*nby+1) exclusive prefix
+    const int* bin_pts;         // (Nj*Ni) flat T indices sorted by bin
+};
+
+struct SeedOut {
+    int2* cell;                 // containing cell {jT,iT}
+    int2* nearest;              // nearest T-point or {-1,-1}  (nullable)
+    int8_t* keep;               // kmask of SeedInit
+    double* dmin;               // haversine distance to the nearest T-point (nullable)
+};
+
+cudaError_t locate_build(int Nj, int Ni, const double* d_lat, const double* d_lon, const double* d_res,
+                         LocateGrid* out, int** owned_start, int** owned_pts, cudaStream_t st);
+cudaError_t launch_seed_locate(const LocateGrid& lg, const AdvectGrid& g, const float* ic0,
+                               long long nP, const pt* SG, const pt* SC, const SeedOut& o,
+                               int do_survive, int do_cell, cudaStream_t st);
+cudaError_t launch_nearest_brute(const LocateGrid& lg, long long nP, const pt* SG, int2* nearest,
+                                 double* dmin, cudaStream_t st);
+
+// ---- batched geometry predicates on explicit coordinates (st_geom.cu) ----------------
+cudaError_t launch_geom_intersect(long long n, const pt* A, const pt* B, const pt* C, const pt* D,
+                                  int8_t* out, cudaStream_t st);
+cudaError_t launch_geom_inside(long long n, const pt* yx, const pt* quads, int8_t* out, cudaStream_t st);
+cudaError_t launch_geom_walk(long long n, const pt* p1, const pt* p2, const pt* ring, const int32_t* kcross_in,
+                             int32_t* kcross, int32_t* knhc, cudaStream_t st);
+cudaError_t launch_geom_survive(long long n, const int32_t* ji, int Nj, int Ni, const int8_t* tm5,
+                                const double* ic5, double rmin_conc, int32_t* out, cudaStream_t st);
+cudaError_t launch_haversine(long long n, double plat, double plon, const double* lat, const double* lon,
+                             double* out, cudaStream_t st);
+
+}  // namespace st

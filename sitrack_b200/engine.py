@@ -1,0 +1,306 @@
+"""TrackEngine -- host-side owner of one GPU's share of the tracking run.
+
+Python here is plumbing only (argument marshalling, CUDA streams/events and
+pinned buffers through PyTorch); all arithmetic of the path happens in
+libsitrack_b200.so.  One engine = one CUDA device = one process (rank).
+
+Reference mapping (paths relative to stephanieleroux/sitrack):
+  TrackEngine(...)        static grid + constants   si3_part_tracker.py:192-202, :31, :37
+  .seed_locate(...)       SeedInit loop             sitrack/tracking.py:120-160
+  .set_buoys(...)         state allocation          si3_part_tracker.py:324-344
+  .step(...)              loop body                 si3_part_tracker.py:378-493
+  .track(...)             record loop               si3_part_tracker.py:361-496
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import as_c, check, hptr
+
+FillValue = -9999.0
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.SitrackCudaError("no CUDA device visible to PyTorch; sitrack_b200 has no CPU fallback")
+    return torch
+
+
+def _dptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _sptr(stream):
+    if stream is None:
+        return None
+    return stream.cuda_stream
+
+
+class TrackEngine:
+    def __init__(self, Yf, Xf, Yu=None, Xu=None, Yv=None, Xv=None, tmask=None, uv_strategy=1,
+                 rdt=3600.0, rmin_conc=0.1, device=0):
+        if tmask is None:
+            raise ValueError("tmask is required")
+        self.L = _lib.lib()
+        self.Nj, self.Ni = tmask.shape
+        self.device = int(device)
+        self.uv_strategy, self.rdt, self.rmin_conc = int(uv_strategy), float(rdt), float(rmin_conc)
+        arrs = [None if a is None else as_c(a, np.float64) for a in (Yf, Xf, Yu, Xu, Yv, Xv)]
+        for a in arrs:
+            if a is not None and a.shape != (self.Nj, self.Ni):
+                raise ValueError("grid arrays must all have shape (Nj,Ni)")
+        tm = as_c(tmask, np.int8)
+        h = C.c_void_p()
+        check(self.L.st_create(C.byref(h), self.device, self.Nj, self.Ni, *[hptr(a) for a in arrs], hptr(tm),
+                               self.uv_strategy, self.rdt, self.rmin_conc))
+        self.h = h
+        self.nP = 0
+        self._nslots = 0
+        self._has_locate = False
+
+    # -- lifecycle ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.st_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- seeding -----------------------------------------------------------------------
+    def set_locate_grid(self, latT, lonT, resKM=None):
+        la, lo = as_c(latT, np.float64), as_c(lonT, np.float64)
+        rk = None if resKM is None or np.shape(resKM) != (self.Nj, self.Ni) else as_c(resKM, np.float64)
+        check(self.L.st_set_locate_grid(self.h, hptr(la), hptr(lo), hptr(rk)), self.h)
+        self._has_locate = True
+
+    def seed_locate(self, SG, SC, ic0):
+        """-> (cell (nP,2) i4, nearest (nP,2) i4, keep (nP,) i1); SeedInit's loop on the device."""
+        SG, SC = as_c(SG, np.float64), as_c(SC, np.float64)
+        ic0 = as_c(ic0, np.float32)
+        nP = SG.shape[0]
+        cell = np.zeros((nP, 2), np.int32)
+        near = np.zeros((nP, 2), np.int32)
+        keep = np.zeros(nP, np.int8)
+        check(self.L.st_seed_locate(self.h, nP, hptr(SG), hptr(SC), hptr(ic0), hptr(cell), hptr(near), hptr(keep)),
+              self.h)
+        return cell, near, keep
+
+    def seed_locate_dev(self, SG_t, SC_t, ic0_t, stream=None):
+        """Device tensors in, device tensors out (async on `stream`)."""
+        torch = _torch()
+        nP = SG_t.shape[0]
+        dev = SG_t.device
+        cell = torch.empty((nP, 2), dtype=torch.int32, device=dev)
+        near = torch.empty((nP, 2), dtype=torch.int32, device=dev)
+        keep = torch.empty((nP,), dtype=torch.int8, device=dev)
+        stream = stream or torch.cuda.current_stream(dev)
+        check(self.L.st_seed_locate_dev(self.h, nP, _dptr(SG_t), _dptr(SC_t), _dptr(ic0_t), _dptr(cell),
+                                        _dptr(near), _dptr(keep), _sptr(stream)), self.h)
+        return cell, near, keep
+
+    def nearest_point(self, latlon, rd_found_km=2.5, max_itr=10, brute=False):
+        ll = as_c(latlon, np.float64).reshape(-1, 2)
+        ji = np.zeros((ll.shape[0], 2), np.int32)
+        d = np.zeros(ll.shape[0], np.float64)
+        check(self.L.st_nearest_point(self.h, ll.shape[0], hptr(ll), rd_found_km, max_itr, int(brute),
+                                      hptr(ji), hptr(d)), self.h)
+        return ji, d
+
+    def find_containing_cell(self, yx, ji_near):
+        yx = as_c(yx, np.float64).reshape(-1, 2)
+        jn = as_c(ji_near, np.int32).reshape(-1, 2)
+        cell = np.zeros_like(jn)
+        found = np.zeros(yx.shape[0], np.int8)
+        check(self.L.st_find_containing_cell(self.h, yx.shape[0], hptr(yx), hptr(jn), hptr(cell), hptr(found)),
+              self.h)
+        return cell, found.astype(bool)
+
+    # -- state -------------------------------------------------------------------------
+    def set_buoys(self, pos, cell, rec_first=None, rec_last=None):
+        pos, cell = as_c(pos, np.float64), as_c(cell, np.int32)
+        rf = None if rec_first is None else as_c(rec_first, np.int32)
+        rl = None if rec_last is None else as_c(rec_last, np.int32)
+        check(self.L.st_set_buoys(self.h, pos.shape[0], hptr(pos), hptr(cell), hptr(rf), hptr(rl)), self.h)
+        self.nP = pos.shape[0]
+
+    def set_buoys_dev(self, pos_t, cell_t, rec_first_t=None, rec_last_t=None, stream=None):
+        torch = _torch()
+        stream = stream or torch.cuda.current_stream(pos_t.device)
+        check(self.L.st_set_buoys_dev(self.h, pos_t.shape[0], _dptr(pos_t), _dptr(cell_t), _dptr(rec_first_t),
+                                      _dptr(rec_last_t), _sptr(stream)), self.h)
+        self.nP = pos_t.shape[0]
+
+    def get_state(self):
+        pos = np.zeros((self.nP, 2), np.float64)
+        cell = np.zeros((self.nP, 2), np.int32)
+        alive = np.zeros(self.nP, np.int8)
+        check(self.L.st_get_state(self.h, hptr(pos), hptr(cell), hptr(alive)), self.h)
+        return pos, cell, alive
+
+    # -- records -----------------------------------------------------------------------
+    def record_slots(self, n):
+        check(self.L.st_record_slots(self.h, int(n)), self.h)
+        self._nslots = max(self._nslots, int(n))
+
+    def staging(self, slot):
+        """numpy view (3,Nj,Ni) f4 of the slot's pinned host buffer: [u_ice, v_ice, siconc]."""
+        p = C.c_void_p()
+        check(self.L.st_record_host_buffer(self.h, slot, C.byref(p)), self.h)
+        buf = (C.c_float * (3 * self.Nj * self.Ni)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float32).reshape(3, self.Nj, self.Ni)
+
+    def record_device_ptr(self, slot):
+        p = C.c_void_p()
+        check(self.L.st_record_device_buffer(self.h, slot, C.byref(p)), self.h)
+        return p.value
+
+    def submit_record(self, slot, stream=None):
+        check(self.L.st_submit_record(self.h, slot, _sptr(stream)), self.h)
+
+    def upload_record(self, slot, host_rec, stream=None):
+        """Async H2D of a whole record from caller-owned host memory: a pinned torch tensor or
+        a C-contiguous numpy array (3,Nj,Ni) f4 laid out [u_ice, v_ice, siconc]."""
+        ptr = host_rec.data_ptr() if hasattr(host_rec, "data_ptr") else hptr(host_rec)
+        check(self.L.st_upload_record(self.h, slot, ptr, _sptr(stream)), self.h)
+
+    # -- the step ----------------------------------------------------------------------
+    def step(self, slot, jrec, out_yx=None, out_latlon=None, out_mask=None, n_alive=None, stream=None):
+        """Enqueue one record for all buoys (async).  out_* are CUDA tensors (nP,2) f8 /
+        (nP,) i1; n_alive a CUDA int64 scalar tensor that gets incremented."""
+        check(self.L.st_step(self.h, slot, int(jrec), _dptr(out_yx), _dptr(out_latlon), _dptr(out_mask),
+                             _dptr(n_alive), _sptr(stream)), self.h)
+
+    def step_multi(self, rec_stack, jrec0, out_yx=None, out_latlon=None, out_mask=None, n_alive=None,
+                   stream=None):
+        """rec_stack: CUDA tensor (nrec,3,Nj,Ni) f4; outputs (nrec,nP,2)/(nrec,nP); one launch."""
+        nrec = rec_stack.shape[0]
+        assert rec_stack.is_contiguous() and tuple(rec_stack.shape[1:]) == (3, self.Nj, self.Ni)
+        check(self.L.st_step_multi(self.h, _dptr(rec_stack), 3 * self.Nj * self.Ni, nrec, int(jrec0),
+                                   _dptr(out_yx), _dptr(out_latlon), _dptr(out_mask), self.nP,
+                                   _dptr(n_alive), _sptr(stream)), self.h)
+
+    def track_record_host(self, jrec, u, v, ic, out_yx=None, out_latlon=None, out_mask=None, want_alive=True):
+        """Synchronous host-buffer form of one loop iteration (H2D + step + D2H)."""
+        na = C.c_int64(0)
+        check(self.L.st_track_record_host(self.h, int(jrec), hptr(u), hptr(v), hptr(ic), hptr(out_yx),
+                                          hptr(out_latlon), hptr(out_mask), C.byref(na) if want_alive else None),
+              self.h)
+        return na.value
+
+    # -- the record loop ---------------------------------------------------------------
+    def track(self, records, nrec, kstrt=0, pos0=None, posG0=None, rec_first=None, want_latlon=True,
+              sink=None, chunk=None, verbose=None):
+        """The record loop (si3_part_tracker.py:361-496), pipelined.
+
+        records: callable k -> (u, v, ic) arrays (Nj,Ni) for record index k (0-based
+                 within the run; file record = k + kstrt), or an array (nrec,3,Nj,Ni) /
+                 tuple of three (nrec,Nj,Ni) arrays.
+        Pipeline per record k: host fills the pinned staging slot k%2 || copy stream H2D ||
+        compute stream k_advect_step || output stream D2H of trajectory row k+1 into
+        pinned host rows.  With sink=None the full (nrec+1,nP,..) series is returned
+        (rows 0 from pos0/posG0); otherwise sink(jt, yx, latlon, mask) is called with
+        pinned row views that are only valid during the call.
+        """
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        nP = self.nP
+        get = _record_getter(records)
+        self.record_slots(2)
+        stg = [self.staging(0), self.staging(1)]
+        s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        NB = 2
+        d_yx = [torch.empty((nP, 2), dtype=torch.float64, device=dev) for _ in range(NB)]
+        d_ll = [torch.empty((nP, 2), dtype=torch.float64, device=dev) for _ in range(NB)] if want_latlon else [None] * NB
+        d_mk = [torch.empty((nP,), dtype=torch.int8, device=dev) for _ in range(NB)]
+        d_na = torch.zeros((nrec,), dtype=torch.int64, device=dev)
+        keep = sink is None
+        if keep:
+            posC = torch.full((nrec + 1, nP, 2), FillValue, dtype=torch.float64).pin_memory()
+            posG = torch.full((nrec + 1, nP, 2), FillValue, dtype=torch.float64).pin_memory()
+            mask = torch.zeros((nrec + 1, nP), dtype=torch.int8).pin_memory()
+            rows = lambda k: (posC[k + 1], posG[k + 1] if want_latlon else None, mask[k + 1])
+        else:
+            h_yx = [torch.empty((nP, 2), dtype=torch.float64).pin_memory() for _ in range(NB)]
+            h_ll = [torch.empty((nP, 2), dtype=torch.float64).pin_memory() for _ in range(NB)]
+            h_mk = [torch.empty((nP,), dtype=torch.int8).pin_memory() for _ in range(NB)]
+            rows = lambda k: (h_yx[k % NB], h_ll[k % NB] if want_latlon else None, h_mk[k % NB])
+        ev_in = [None] * nrec
+        ev_step = [None] * nrec
+        ev_out = [None] * nrec
+
+        def drain(k):
+            ev_out[k].synchronize()
+            if not keep:
+                y, l, m = rows(k)
+                sink(k, y.numpy(), None if l is None else l.numpy(), m.numpy())
+
+        for k in range(nrec):
+            b = k % 2
+            if k >= 2:
+                ev_in[k - 2].synchronize()                 # staging slot b has left the host
+            u, v, ic = get(k)
+            stg[b][0], stg[b][1], stg[b][2] = u, v, ic     # f4 copy into pinned memory
+            if k >= 2:
+                s_in.wait_event(ev_step[k - 2])            # device slot b no longer read
+            self.submit_record(b, s_in)
+            ev_in[k] = torch.cuda.Event(); ev_in[k].record(s_in)
+            s_cmp.wait_event(ev_in[k])
+            if k >= NB:
+                s_cmp.wait_event(ev_out[k - NB])           # device out buffer b drained
+            self.step(b, k + kstrt, d_yx[b], d_ll[b], d_mk[b], d_na[k:k + 1], s_cmp)
+            ev_step[k] = torch.cuda.Event(); ev_step[k].record(s_cmp)
+            s_out.wait_event(ev_step[k])
+            if not keep and k >= NB:
+                drain(k - NB)                              # pinned row buffer b is free again
+            y, l, m = rows(k)
+            with torch.cuda.stream(s_out):
+                y.copy_(d_yx[b], non_blocking=True)
+                if want_latlon:
+                    l.copy_(d_ll[b], non_blocking=True)
+                m.copy_(d_mk[b], non_blocking=True)
+            ev_out[k] = torch.cuda.Event(); ev_out[k].record(s_out)
+        for k in range(max(0, nrec - NB), nrec):
+            if keep:
+                ev_out[k].synchronize()
+            else:
+                drain(k)
+        torch.cuda.synchronize(dev)
+        n_alive = d_na.cpu().numpy()
+        if not keep:
+            return dict(n_alive=n_alive)
+        posC, posG, mask = posC.numpy(), posG.numpy(), mask.numpy()
+        if pos0 is not None:
+            if rec_first is None:
+                posC[0] = pos0; mask[0] = 1
+                if posG0 is not None:
+                    posG[0] = posG0
+            else:                                           # si3_part_tracker.py:335-340
+                for b in range(nP):
+                    k0 = int(rec_first[b]) - kstrt
+                    if k0 == 0:
+                        posC[0, b] = pos0[b]; mask[0, b] = 1
+                        if posG0 is not None:
+                            posG[0, b] = posG0[b]
+        return dict(posC=posC, posG=posG, mask=mask, n_alive=n_alive)
+
+
+def _record_getter(records):
+    if callable(records):
+        return records
+    if isinstance(records, (tuple, list)) and len(records) == 3:
+        U, V, IC = records
+        return lambda k: (U[k], V[k], IC[k])
+    arr = records
+    return lambda k: (arr[k, 0], arr[k, 1], arr[k, 2])

@@ -1,0 +1,249 @@
+"""GPU: the CUDA path (through the C ABI) against (1) the committed golden fixtures made by
+the reference's own functions and (2) the C oracle on larger seeded inputs.
+
+Bars: cell indices, alive flags, masks, alive counts and f8 positions bit-exact (every
+operation is an un-fused IEEE double op in the reference's order); lat/lon within
+1e-9 degrees of the PROJ-style iterative inverse (PROJ itself iterates to 1e-10 rad).
+"""
+import numpy as np
+import pytest
+
+from conftest import TRACK_CASES, engine_for
+
+pytestmark = pytest.mark.gpu
+
+LATLON_TOL_DEG = 1e-9
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def sit():
+    import sitrack_b200
+    return sitrack_b200
+
+
+# ---- scalar / batched predicates against the reference's golden answers -------------------
+
+def test_inside_quad_golden(sit, gold_pred):
+    G = gold_pred
+    assert [sit.IsInsideQuadrangle(p[0], p[1], G["kat_quad"]) for p in G["kat_pts"]] == [True, False, False, True]
+    got = sit.IsInsideQuadrangleBatch(G["sq_pts"], np.repeat(G["sq_quad"][None], len(G["sq_pts"]), 0))
+    assert np.array_equal(got, G["sq_inside"])
+    assert np.array_equal(sit.IsInsideQuadrangleBatch(G["rq_pts"], G["rq_quads"]), G["rq_inside"])
+
+
+def test_intersect_golden(sit, gold_pred):
+    S = gold_pred["seg_pts"]
+    got = sit.intersect2SegBatch(S[:, 0], S[:, 1], S[:, 2], S[:, 3])
+    assert np.array_equal(got, gold_pred["seg_hit"])
+    assert sit.intersect2Seg(*S[0]) == bool(gold_pred["seg_hit"][0])
+
+
+def test_cell_walk_golden(sit, gold_pred):
+    G = gold_pred
+    Yf, Xf = G["g_Yf"], G["g_Xf"]
+    for k in range(0, len(G["walk_jT"]), 7):
+        jT, iT = int(G["walk_jT"][k]), int(G["walk_iT"][k])
+        V = np.array([[jT - 1, jT - 1, jT, jT], [iT - 1, iT, iT, iT - 1]])
+        kc = sit.CrossedEdge(G["walk_p1"][k], G["walk_p2"][k], V, Yf, Xf)
+        assert kc == G["walk_cross"][k]
+        assert sit.NewHostCell(kc, G["walk_p1"][k], G["walk_p2"][k], V, Yf, Xf) == G["walk_newcell"][k]
+
+
+def test_survive_golden(sit, gold_pred, gold_track):
+    G = gold_pred
+    ic = np.zeros(G["g_tmask"].shape); ic[:, :] = gold_track[0]["IC"][7]
+    got = sit.SurviveBatch(np.stack([G["sv_jT"], G["sv_iT"]], 1), G["g_tmask"], ic)
+    assert np.array_equal(got, G["sv_kill"])
+    assert sit.Survive(1, [int(G["sv_jT"][20]), int(G["sv_iT"][20])], G["g_tmask"], pIceC=ic) == G["sv_kill"][20]
+    with pytest.raises(UnboundLocalError):
+        sit.Survive(1, [5, 5], G["g_tmask"])
+
+
+def test_haversine_golden(sit, gold_pred):
+    G = gold_pred
+    for p, want in zip(G["hav_pts"][:16], G["hav_d"][:16]):
+        assert np.allclose(sit.Haversine(p[0], p[1], G["hav_glat"], G["hav_glon"]), want, rtol=0, atol=1e-9)
+
+
+# ---- the record loop against the reference's golden trajectories ----------------------------
+
+def _run_engine(torch, g, U, V, IC, pos0, cell0, kstrt=0, first=None, last=None, uv_strategy=1, multi=False):
+    nrec = U.shape[0]
+    nP = pos0.shape[0]
+    dev = torch.device("cuda", 0)
+    with engine_for(g, uv_strategy=uv_strategy) as eng:
+        eng.set_buoys(pos0, cell0, first, last)
+        yx = torch.empty((nrec, nP, 2), dtype=torch.float64, device=dev)
+        ll = torch.empty((nrec, nP, 2), dtype=torch.float64, device=dev)
+        mk = torch.empty((nrec, nP), dtype=torch.int8, device=dev)
+        na = torch.zeros((nrec,), dtype=torch.int64, device=dev)
+        cells = np.zeros((nrec + 1, nP, 2), np.int32); alive = np.zeros((nrec + 1, nP), np.int8)
+        cells[0] = cell0; alive[0] = 1
+        if multi:
+            rec = torch.from_numpy(np.stack([U, V, IC], axis=1).astype(np.float32)).to(dev).contiguous()
+            eng.step_multi(rec, kstrt, yx, ll, mk, na)
+            torch.cuda.synchronize()
+            _, c, a = eng.get_state()
+            cells[-1], alive[-1] = c, a
+        else:
+            eng.record_slots(1)
+            for k in range(nrec):
+                st = eng.staging(0)
+                st[0], st[1], st[2] = U[k], V[k], IC[k]
+                eng.submit_record(0)
+                eng.step(0, k + kstrt, yx[k], ll[k], mk[k], na[k:k + 1])
+                torch.cuda.synchronize()
+                _, c, a = eng.get_state()
+                cells[k + 1], alive[k + 1] = c, a
+        return yx.cpu().numpy(), ll.cpu().numpy(), mk.cpu().numpy(), na.cpu().numpy(), cells, alive
+
+
+@pytest.mark.parametrize("multi", [False, True])
+@pytest.mark.parametrize("name", list(TRACK_CASES))
+def test_track_golden(torch, corc, gold_track, name, multi):
+    T, g = gold_track
+    c = TRACK_CASES[name]
+    s = np.float32(c["scale"])
+    first = T["win_first"] if c["win"] else None
+    last = T["win_last"] if c["win"] else None
+    yx, ll, mk, na, cells, alive = _run_engine(torch, g, s * T["U"], s * T["V"], T["IC"], T["pos0"],
+                                               T["jiT0"], c["kstrt"], first, last, c["uv_strategy"], multi)
+    assert np.array_equal(yx, T[name + "_posC"][1:])                 # bit-exact positions, fill rows included
+    assert np.array_equal(mk, T[name + "_mask"][1:])
+    assert np.array_equal(na, T[name + "_nalive"])
+    if multi:
+        assert np.array_equal(cells[-1], T[name + "_jiT"][-1]) and np.array_equal(alive[-1], T[name + "_alive"][-1])
+    else:
+        assert np.array_equal(cells, T[name + "_jiT"])               # cell index per buoy per record
+        assert np.array_equal(alive, T[name + "_alive"])
+    want = corc.inv_stere(T[name + "_posC"][1:].reshape(-1, 2)).reshape(ll.shape)
+    assert np.abs(ll - want).max() < LATLON_TOL_DEG                  # also for the -9999 rows (:493)
+
+
+def test_track_host_call_and_pipeline(torch, gold_track):
+    """The host-buffer entry point (what a reference-side binding calls per record) and the
+    pipelined engine.track() give the same rows as the golden run."""
+    T, g = gold_track
+    nrec, nP = T["U"].shape[0], T["pos0"].shape[0]
+    with engine_for(g) as eng:
+        eng.set_buoys(T["pos0"], T["jiT0"])
+        yx = np.empty((nP, 2)); ll = np.empty((nP, 2)); mk = np.empty(nP, np.int8)
+        for k in range(nrec):
+            na = eng.track_record_host(k, T["U"][k], T["V"][k], T["IC"][k], yx, ll, mk)
+            assert na == T["uv1_nalive"][k]
+            assert np.array_equal(yx, T["uv1_posC"][k + 1]) and np.array_equal(mk, T["uv1_mask"][k + 1])
+    with engine_for(g) as eng:
+        eng.set_buoys(T["pos0"], T["jiT0"])
+        r = eng.track((T["U"], T["V"], T["IC"]), nrec, pos0=T["pos0"], posG0=T["posG0"])
+        assert np.array_equal(r["posC"], T["uv1_posC"]) and np.array_equal(r["mask"], T["uv1_mask"])
+        assert np.array_equal(r["n_alive"], T["uv1_nalive"])
+        rows = []
+        eng.set_buoys(T["pos0"], T["jiT0"])
+        eng.track((T["U"], T["V"], T["IC"]), nrec, sink=lambda k, y, l, m: rows.append((k, y.copy(), m.copy())))
+        assert [k for k, _, _ in rows] == list(range(nrec))
+        assert all(np.array_equal(y, T["uv1_posC"][k + 1]) for k, y, _ in rows)
+
+
+# ---- seeding ------------------------------------------------------------------------------------
+
+def test_seedinit_golden(sit, gold_seed):
+    S, g = gold_seed
+    ic = np.zeros(g["tmask"].shape); ic[:, :] = S["ic0"]
+    nP, pSG, pSC, pIDs, zjiT, zV, iKeep = sit.SeedInit(S["ids"].copy(), S["SG"], S["SC"], g["latT"], g["lonT"],
+                                                       g["Yf"], g["Xf"], g["ResKM"], g["tmask"], xIceConc=ic)
+    assert nP == int(S["out_nP"]) and np.array_equal(iKeep, S["out_iKeep"])
+    assert np.array_equal(zjiT, S["out_jiT"]) and np.array_equal(zV, S["out_VRTCS"])
+    assert np.array_equal(pSG, S["out_SG"]) and np.array_equal(pSC, S["out_SC"]) and np.array_equal(pIDs, S["out_IDs"])
+
+
+def test_nearest_point_hash_vs_brute_vs_golden(sit, gold_seed):
+    S, g = gold_seed
+    ji_h, d_h = sit.NearestPointBatch(S["SG"], g["latT"], g["lonT"], 2.5, g["ResKM"], 10)
+    assert np.array_equal(ji_h, S["out_nearest"])
+    # exactness of the hash search: unconditional argmin (max_itr=1 accepts anything) == whole-grid scan
+    ji_a, d_a = sit.NearestPointBatch(S["SG"], g["latT"], g["lonT"], 2.5, g["ResKM"], 1)
+    ji_b, d_b = sit.NearestPointBatch(S["SG"], g["latT"], g["lonT"], 2.5, g["ResKM"], 1, brute=True)
+    assert np.array_equal(ji_a, ji_b) and np.array_equal(d_a, d_b)
+    k = int(np.flatnonzero(S["out_nearest"][:, 0] >= 0)[0])
+    assert sit.NearestPoint(tuple(S["SG"][k]), g["latT"], g["lonT"], rd_found_km=2.5, resolkm=g["ResKM"],
+                            max_itr=10) == tuple(S["out_nearest"][k])
+    lPin, ji, vr = sit.FindContainingCell(tuple(S["SC"][S["out_iKeep"][0]]), tuple(S["out_nearest"][S["out_iKeep"][0]]),
+                                          g["Yf"], g["Xf"])
+    assert lPin and ji == list(S["out_jiT"][0]) and np.array_equal(np.array(vr), S["out_VRTCS"][0])
+
+
+# ---- larger seeded inputs against the C oracle ------------------------------------------------------
+
+@pytest.mark.parametrize("preset,khss,nrec,scale", [("small", 1, 72, 1.0), ("nanuk4", 5, 24, 1.0),
+                                                     ("nanuk4", 2, 48, 3.0)])
+def test_track_vs_oracle(torch, corc, preset, khss, nrec, scale):
+    import synth
+    g = synth.make_grid(**synth.GRID_PRESETS[preset], seed=0)
+    U, V, IC = synth.make_records(g, nrec, seed=1)
+    U *= np.float32(scale); V *= np.float32(scale)
+    ids, SG, SC = synth.hss_seeds(g, IC[0], khss=khss)
+    with engine_for(g) as eng:
+        eng.set_locate_grid(g["latT"], g["lonT"], g["ResKM"])
+        cell, near, keep = eng.seed_locate(SG, SC, IC[0])
+    # seeds sit on T-points: the nearest point is that T-point and the containing cell is its own
+    jj, ii = np.where(g["tmask"][::khss, ::khss].astype(bool) & (g["latT"][::khss, ::khss] >= 55.) & (IC[0][::khss, ::khss] >= 0.9))
+    assert np.array_equal(near[:, 0], jj * khss) and np.array_equal(near[:, 1], ii * khss)
+    ik = np.flatnonzero(keep)
+    pos0, cell0 = SC[ik], cell[ik]
+    assert np.array_equal(cell0, near[ik])
+    ref = corc.track(g, U, V, IC, pos0, cell0.astype(np.int64))
+    for multi in (False, True):
+        yx, ll, mk, na, cells, alive = _run_engine(torch, g, U, V, IC, pos0, cell0, multi=multi)
+        assert np.array_equal(yx, ref["posC"][1:]) and np.array_equal(mk, ref["mask"][1:])
+        assert np.array_equal(na, ref["nalive"])
+        assert np.array_equal(cells[-1], ref["jiT"]) and np.array_equal(alive[-1], ref["alive"])
+        if not multi:
+            assert np.array_equal(cells, ref["jiT_hist"]) and np.array_equal(alive, ref["alive_hist"])
+        assert np.abs(ll - ref["posG"][1:]).max() < LATLON_TOL_DEG
+    assert ref["ncross"] > 0 and ref["alive"].sum() < ik.size or nrec < 48
+
+
+def test_seed_locate_scattered_vs_oracle(corc):
+    import synth
+    g = synth.make_grid(**synth.GRID_PRESETS["small"], seed=4)
+    _, _, IC = synth.make_records(g, 1, seed=5)
+    ids, SG, SC = synth.scattered_seeds(g, 3000, seed=6)
+    jiT, keep, near = corc.seed_init(SG, SC, g["latT"], g["lonT"], g["Yf"], g["Xf"], g["ResKM"], g["tmask"], IC[0])
+    with engine_for(g) as eng:
+        eng.set_locate_grid(g["latT"], g["lonT"], g["ResKM"])
+        cell, near_g, keep_g = eng.seed_locate(SG, SC, IC[0])
+    assert np.array_equal(near_g, near)
+    assert np.array_equal(keep_g, keep)
+    ik = np.flatnonzero(keep)
+    assert np.array_equal(cell[ik], jiT[ik]) and 0 < ik.size < 3000
+
+
+def test_projection_kernels(sit, corc):
+    rng = np.random.default_rng(8)
+    yx = rng.uniform(-4500, 4500, (5000, 2))
+    yx[0] = [0.0, 0.0]; yx[1] = [-9999.0, -9999.0]
+    ll = sit.CartNPSkm2Geo1D(yx)
+    assert np.abs(ll - corc.inv_stere(yx)).max() < LATLON_TOL_DEG
+    back = sit.Geo2CartNPSkm1D(ll[2:])
+    assert np.abs(back - yx[2:]).max() < 1e-6                        # km
+    Y, X = sit.ConvertGeo2CartesianNPSkm(ll[2:, 0].reshape(2, -1), ll[2:, 1].reshape(2, -1))
+    assert Y.shape == (2, 2499) and np.abs(Y.ravel() - yx[2:, 0]).max() < 1e-6
+
+
+def test_empty_and_errors(sit, gold_track):
+    T, g = gold_track
+    with engine_for(g) as eng:
+        eng.set_buoys(np.zeros((0, 2)), np.zeros((0, 2), np.int32))
+        assert eng.track_record_host(0, T["U"][0], T["V"][0], T["IC"][0]) == 0
+        with pytest.raises(sit.SitrackCudaError):
+            eng.step(5, 0)                                          # slot out of range
+        with pytest.raises(sit.SitrackCudaError):
+            eng.seed_locate(np.zeros((1, 2)), np.zeros((1, 2)), T["IC"][0])   # no locate grid yet
+    assert sit.IsInsideQuadrangleBatch(np.zeros((0, 2)), np.zeros((0, 4, 2))).shape == (0,)

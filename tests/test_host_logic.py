@@ -1,0 +1,79 @@
+"""CPU: host-side logic of the drop-in surface (no GPU arithmetic involved), checked against
+the reference's own functions when /root/reference is present, and against pinned values."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+import sitrack_b200 as sit
+from oracle import ref_loader
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def test_constants():
+    assert sit.rmin_conc == 0.1 and sit.rFoundKM == 2.5 and sit.FillValue == -9999.
+    assert sit.tunits_default == 'seconds since 1970-01-01 00:00:00'
+
+
+def test_epoch_clock():
+    assert sit.epoch2clock(850608000) == "1996-12-15_00:00:00"
+    assert sit.epoch2clock(850608000, precision='h') == "1996-12-15_00"
+    assert sit.clock2epoch("1996-12-15_00:00:00") == 850608000
+    assert sit.clock2epoch("1997-04-20", precision='D', cfrmt='guess') == 861494400
+
+
+def test_updt_ind_in_place():
+    for k, (dj, di) in {1: (-1, 0), 2: (0, 1), 3: (1, 0), 4: (0, -1), 5: (-1, -1), 6: (-1, 1), 7: (1, 1), 8: (1, -1)}.items():
+        V = np.array([[9, 9, 10, 10], [19, 20, 20, 19]]); ji = np.array([10, 20])
+        V2, ji2 = sit.UpdtInd4NewCell(k, V, ji)
+        assert V2 is V and ji2 is ji                               # mutated in place, like the reference
+        assert list(ji) == [10 + dj, 20 + di]
+        assert np.array_equal(V, [[9 + dj, 9 + dj, 10 + dj, 10 + dj], [19 + di, 20 + di, 20 + di, 19 + di]])
+    with pytest.raises(SystemExit):
+        quiet(sit.UpdtInd4NewCell, 9, np.zeros((2, 4), int), np.zeros(2, int))
+
+
+def test_get_time_span_pinned():
+    t = 850608000 + 1800 + 3600 * np.arange(100)
+    Nt, k0, kN, a, b = quiet(sit.GetTimeSpan, 3600., t, 850608000, t[0], t[-1])
+    assert (Nt, k0, kN) == (100, 0, 99)
+    Nt, k0, kN, a, b = quiet(sit.GetTimeSpan, 3600., t, 850608000 + 7200, t[0], t[-1], iStop=850608000 + 36000)
+    assert (k0, kN, Nt) == (2, 9, 8)                               # ties in argmin resolve to the first minimum
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="upstream reference not present")
+def test_against_reference_host_functions():
+    ref = ref_loader.load()
+    rng = np.random.default_rng(0)
+    t = 850608000 + 1800 + 3600 * np.arange(240)
+    for _ in range(50):
+        seed = int(850608000 + rng.integers(0, 200) * 3600 + rng.integers(0, 3600))
+        stop = int(seed + rng.integers(1, 30) * 3600) if rng.random() < 0.7 else None
+        assert quiet(sit.GetTimeSpan, 3600., t, seed, t[0], t[-1], iStop=stop) == \
+            quiet(ref.GetTimeSpan, 3600., t, seed, t[0], t[-1], iStop=stop)
+    for k in range(1, 9):
+        V = rng.integers(5, 50, (2, 4)); ji = rng.integers(5, 50, 2)
+        a = sit.UpdtInd4NewCell(k, V.copy(), ji.copy()); b = ref.UpdtInd4NewCell(k, V.copy(), ji.copy())
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(sit.debugSeeding(), ref.debugSeeding())
+    x = rng.uniform(0, 360, 20)
+    assert np.allclose(sit.degE_to_degWE(x), ref.degE_to_degWE(x)) and sit.degE_to_degWE(270.) == ref.degE_to_degWE(270.)
+    for it in (0, 850608000, 861494399):
+        for p in "smhD":
+            assert sit.epoch2clock(it, precision=p) == ref.epoch2clock(it, precision=p)
+    msk = (rng.random((40, 30)) > 0.2).astype('i1'); lat = rng.uniform(50, 90, (40, 30)); lon = rng.uniform(0, 360, (40, 30))
+    ic = rng.random((40, 30))
+    for kh in (1, 3):
+        assert np.array_equal(sit.nemoSeed(msk, lat, lon, ic, khss=kh), ref.nemoSeed(msk, lat, lon, ic, khss=kh))
+    a = quiet(sit.nemoSeed, msk, lat, lon, ic, khss=1, platF=lat + 0.1, plonF=lon + 0.1)
+    b = quiet(ref.nemoSeed, msk, lat, lon, ic, khss=1, platF=lat + 0.1, plonF=lon + 0.1)
+    assert np.array_equal(a, b)
+    import os
+    dat = os.path.join(os.path.dirname(os.path.dirname(ref.__file__)), "tools", "sidfexloc.dat")
+    ll, ids = quiet(sit.SidfexSeeding, dat); ll2, ids2 = quiet(ref.SidfexSeeding, dat)
+    assert np.array_equal(ll, ll2) and np.array_equal(ids, ids2)
