@@ -55,6 +55,10 @@ int  st_create(st_ctx **out, int device, int Nj, int Ni,
                int uv_strategy, double rdt, double rmin_conc);
 void st_destroy(st_ctx *ctx);
 
+/* 0 (default) = tuned k_advect_step, 1 = k_advect_step_v1, the straightforward kernel kept as
+ * A/B reference (also selected by the environment variable SITRACK_B200_KERNEL=v1).     */
+int  st_set_kernel_variant(st_ctx *ctx, int variant);
+
 /* Polar-stereographic parameters of CartNPSkm2Geo1D (util.py:413: lat0=70, lon0=-45). */
 int  st_set_projection(st_ctx *ctx, double lat_ts_deg, double lon0_deg);
 
@@ -157,6 +161,11 @@ int  st_survive(int device, int64_t n, const int32_t *ji, int Nj, int Ni, const 
                 const double *ic5, double rmin_conc, int32_t *kill);
 int  st_haversine(int device, int64_t n, double plat, double plon, const double *lat, const double *lon,
                   double *out_km);
+
+/* Diagnostics: the step kernel divides displacements by 1000 (si3_part_tracker.py:457-458)
+ * with a reciprocal + exact-residual sequence; q_fast is that result, q_div the IEEE
+ * division, for n host values a.                                                          */
+int  st_selftest_div1000(int device, int64_t n, const double *a, double *q_fast, double *q_div);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,8 @@ SIGNATURES = {
     "st_create": (c_int, [C.POINTER(vp), c_int, c_int, c_int] + [vp] * 7 + [c_int, c_dbl, c_dbl]),
     "st_destroy": (None, [vp]),
     "st_set_projection": (c_int, [vp, c_dbl, c_dbl]),
+    "st_set_kernel_variant": (c_int, [vp, c_int]),
+    "st_selftest_div1000": (c_int, [c_int, c_i64, vp, vp, vp]),
     "st_set_locate_grid": (c_int, [vp, vp, vp, vp]),
     "st_seed_locate": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp]),
     "st_seed_locate_dev": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp]),

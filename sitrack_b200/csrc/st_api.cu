@@ -6,6 +6,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -26,6 +27,7 @@ struct st_ctx {
     int8_t* tmask = nullptr;
     double *latT = nullptr, *lonT = nullptr, *resKM = nullptr;
     int *bin_start = nullptr, *bin_pts = nullptr;
+    AngEntry* atab = nullptr;
     LocateGrid lg{};
     bool has_locate = false;
     // buoys
@@ -33,6 +35,7 @@ struct st_ctx {
     pt* pos = nullptr; int2* cell = nullptr; int8_t* alive = nullptr;
     int32_t *rec_first = nullptr, *rec_last = nullptr;
     bool has_window = false;
+    int variant = 0;            // 0 = tuned k_advect_step, 1 = k_advect_step_v1 (A/B reference)
     // host-API scratch outputs
     pt *o_yx = nullptr, *o_ll = nullptr; int8_t* o_mask = nullptr; unsigned long long* o_nalive = nullptr;
     long long capOut = 0;
@@ -123,6 +126,30 @@ static cudaError_t upload_pts(pt** dst, const double* Y, const double* X, size_t
     return upload(dst, tmp.data(), n);
 }
 
+// lat/lon of the fill point (-9999,-9999) km, computed by the device's own inverse: rows of idle
+// buoys carry it (si3_part_tracker.py:493 converts every row, fill rows included)
+static cudaError_t refresh_fill(st_ctx* c)
+{
+    double* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 4 * sizeof(double));
+    if (e != cudaSuccess) return e;
+    const double h[2] = {ST_FILL, ST_FILL};
+    double out[2] = {0, 0};
+    e = cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_xy2latlon((const pt*)d, (pt*)(d + 2), 1, c->grid.proj, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d + 2, sizeof(out), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    c->grid.proj.fill_lat = out[0]; c->grid.proj.fill_lon = out[1];
+    return e;
+}
+
+static cudaError_t make_angle_table(AngEntry** dst)
+{
+    std::vector<AngEntry> t(47);
+    for (int j = 0; j < 47; ++j) { const double a = j / 64.0; t[j].alpha = asin(a); t[j].ca = sqrt(1.0 - a * a); t[j].sa = a; t[j].pad = 0.0; }
+    return upload(dst, t.data(), t.size());
+}
+
 struct Scratch {                       // RAII device scratch for the host-array helpers
     std::vector<void*> p;
     ~Scratch() { for (void* q : p) cudaFree(q); }
@@ -163,7 +190,19 @@ int st_create(st_ctx** out, int device, int Nj, int Ni, const double* Yf, const 
     c->grid.Nj = Nj; c->grid.Ni = Ni; c->grid.uv_strategy = uv_strategy; c->grid.rdt = rdt;
     c->grid.rmin_conc = rmin_conc; c->grid.F = c->F; c->grid.U = c->U; c->grid.V = c->V; c->grid.tmask = c->tmask;
     c->grid.proj = make_proj(70.0, -45.0);
+    e = make_angle_table(&c->atab);
+    c->grid.atab = c->atab;
+    if (e == cudaSuccess) e = refresh_fill(c);
+    if (e != cudaSuccess) { rc = cuda_fail(nullptr, e, "st_create(projection tables)"); st_destroy(c); return rc; }
+    { const char* ev = getenv("SITRACK_B200_KERNEL"); if (ev && ev[0] == 'v' && ev[1] == '1') c->variant = 1; }
     *out = c;
+    return ST_OK;
+}
+
+int st_set_kernel_variant(st_ctx* c, int variant)
+{
+    if (!c || variant < 0 || variant > 1) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 (tuned) or 1 (v1)");
+    c->variant = variant;
     return ST_OK;
 }
 
@@ -171,7 +210,7 @@ void st_destroy(st_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->F); cudaFree(c->U); cudaFree(c->V); cudaFree(c->tmask);
+    cudaFree(c->F); cudaFree(c->U); cudaFree(c->V); cudaFree(c->tmask); cudaFree(c->atab);
     cudaFree(c->latT); cudaFree(c->lonT); cudaFree(c->resKM); cudaFree(c->bin_start); cudaFree(c->bin_pts);
     cudaFree(c->pos); cudaFree(c->cell); cudaFree(c->alive); cudaFree(c->rec_first); cudaFree(c->rec_last);
     cudaFree(c->o_yx); cudaFree(c->o_ll); cudaFree(c->o_mask); cudaFree(c->o_nalive);
@@ -185,6 +224,8 @@ int st_set_projection(st_ctx* c, double lat_ts_deg, double lon0_deg)
 {
     if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
     c->grid.proj = make_proj(lat_ts_deg, lon0_deg);
+    CU(c, cudaSetDevice(c->device));
+    CU(c, refresh_fill(c));
     return ST_OK;
 }
 
@@ -470,7 +511,7 @@ int st_step(st_ctx* c, int slot, int jrec, double* out_yx, double* out_latlon, i
     const size_t npt = (size_t)c->Nj * c->Ni;
     const float* r = c->d_rec[slot];
     StepOut o{(pt*)out_yx, (pt*)out_latlon, out_mask, (unsigned long long*)n_alive};
-    CU(c, launch_advect_step(c->grid, r, r + npt, r + 2 * npt, state_of(c), jrec, o, (cudaStream_t)stream));
+    CU(c, launch_advect_step(c->grid, r, r + npt, r + 2 * npt, state_of(c), jrec, o, c->variant, (cudaStream_t)stream));
     return ST_OK;
 }
 
@@ -516,7 +557,7 @@ int st_track_record_host(st_ctx* c, int jrec, const float* u, const float* v, co
     if (n_alive) CU(c, cudaMemsetAsync(c->o_nalive, 0, sizeof(unsigned long long), s));
     StepOut o{out_yx ? c->o_yx : nullptr, out_latlon ? c->o_ll : nullptr, out_mask ? c->o_mask : nullptr,
               n_alive ? c->o_nalive : nullptr};
-    CU(c, launch_advect_step(c->grid, d, d + npt, d + 2 * npt, state_of(c), jrec, o, s));
+    CU(c, launch_advect_step(c->grid, d, d + npt, d + 2 * npt, state_of(c), jrec, o, c->variant, s));
     if (c->nP > 0) {
         if (out_yx) CU(c, cudaMemcpyAsync(out_yx, c->o_yx, sizeof(pt) * c->nP, cudaMemcpyDeviceToHost, s));
         if (out_latlon) CU(c, cudaMemcpyAsync(out_latlon, c->o_ll, sizeof(pt) * c->nP, cudaMemcpyDeviceToHost, s));
@@ -560,6 +601,19 @@ int st_latlon2xy(int device, int64_t n, const double* latlon, double* yx, double
     CUS(s.up(&a, latlon, (size_t)2 * n)); CUS(s.alloc(&b, (size_t)2 * n));
     CUS(launch_latlon2xy((const pt*)a, (pt*)b, n, make_proj_fwd(lat_ts, lon0), 0));
     CUS(cudaMemcpy(yx, b, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_selftest_div1000(int device, int64_t n, const double* a, double* q_fast, double* q_div)
+{
+    if (n < 0 || !a || !q_fast || !q_div) return fail(nullptr, ST_EINVAL, "st_selftest_div1000: NULL argument");
+    int rc = use_device(nullptr, device); if (rc) return rc;
+    if (n == 0) return ST_OK;
+    Scratch s; double *d, *f, *r;
+    CUS(s.up(&d, a, (size_t)n)); CUS(s.alloc(&f, (size_t)n)); CUS(s.alloc(&r, (size_t)n));
+    CUS(launch_div1000(d, f, r, n, 0));
+    CUS(cudaMemcpy(q_fast, f, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CUS(cudaMemcpy(q_div, r, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return ST_OK;
 }
 

@@ -123,6 +123,7 @@ struct ProjConst {
     double k_t;        // 1000 / (a * akm1): km radius -> t = tan(pi/4 - chi/2)
     double c[6];       // series coefficients of sin(2k chi), k = 1..6
     double lon0_rad;   // central longitude
+    double fill_lat, fill_lon;   // inv_stere of (-9999,-9999) km: what rows of idle buoys hold (:493)
 };
 
 __device__ __forceinline__ pt inv_stere(pt yx, const ProjConst& pc)
@@ -144,6 +145,83 @@ __device__ __forceinline__ pt inv_stere(pt yx, const ProjConst& pc)
     if (lam > PI) lam -= 2.0 * PI;
     if (lam < -PI) lam += 2.0 * PI;
     pt r; r.y = phi * R2D; r.x = lam * R2D; return r;     // [lat, lon] degrees
+}
+
+// ---- fast inverse for the fused step (same map as inv_stere, fewer FP64-pipe slots) ------
+// angle of a unit vector from a 47-entry table: the octant-folded sine m = min(|s|,|c|) selects
+// alpha_j = asin(j/64); the remainder delta (|delta| < 0.011) comes from sin(delta) =
+// m cos(alpha_j) - M sin(alpha_j) and a 4-term asin series (error < 1e-19 rad).
+struct __align__(16) AngEntry { double alpha, ca, sa, pad; };
+
+__device__ __forceinline__ double rcp_nr(double d)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0); y = fma(y, e, y);
+    e = fma(-d, y, 1.0);        y = fma(y, e, y);
+    return y;
+}
+__device__ __forceinline__ double rsqrt_nr(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-(x * y), y, 1.0); y = fma(0.5 * y, e, y);
+    e = fma(-(x * y), y, 1.0);        y = fma(0.5 * y, e, y);
+    return y;
+}
+__device__ __forceinline__ double angle_of_unit(double s, double c, const AngEntry* __restrict__ tab)
+{
+    const double HALFPI = 1.5707963267948966, PI = 3.141592653589793;
+    const double a = fabs(s), b = fabs(c);
+    const bool swp = a > b;
+    const double m = swp ? b : a, M = swp ? a : b;
+    int j = __double2int_rn(m * 64.0);
+    j = min(max(j, 0), 46);
+    const double2 e0 = __ldg(reinterpret_cast<const double2*>(tab + j));          // alpha, cos
+    const double sa = __ldg(reinterpret_cast<const double*>(tab + j) + 2);         // sin
+    const double sd = fma(m, e0.y, -(M * sa));
+    const double z = sd * sd;
+    const double d = fma(sd * z, fma(z, fma(z, 15. / 336., 3. / 40.), 1. / 6.), sd);
+    double th = e0.x + d;
+    if (swp) th = HALFPI - th;
+    if (c < 0.0) th = PI - th;
+    return copysign(th, s);
+}
+
+__device__ __forceinline__ pt inv_stere_fast(pt yx, const ProjConst& pc, const AngEntry* __restrict__ tab)
+{
+    const double PI = 3.141592653589793, R2D = 57.29577951308232;
+    const double r2 = fma(yx.x, yx.x, yx.y * yx.y);
+    const double rinv = (r2 > 0.0) ? rsqrt_nr(r2) : 0.0;          // pole: lam = 0 like PROJ
+    const double t = (r2 * rinv) * pc.k_t;
+    const double t2 = t * t;
+    const double inv = rcp_nr(1.0 + t2);
+    const double s = (1.0 - t2) * inv;              // sin(chi)
+    const double c = (t + t) * inv;                 // cos(chi)
+    const double chi = angle_of_unit(s, c, tab);
+    const double s2 = (s + s) * c;                  // sin(2 chi)
+    const double c2x2 = fma(-4.0 * s, s, 2.0);      // 2 cos(2 chi)
+    double b2 = 0.0, b1 = pc.c[4];                  // c[5] = 6e-16 rad is dropped
+#pragma unroll
+    for (int k = 3; k >= 0; --k) { const double b0 = fma(c2x2, b1, pc.c[k] - b2); b2 = b1; b1 = b0; }
+    const double phi = fma(b1, s2, chi);
+    double lam = angle_of_unit(yx.x * rinv, -(yx.y * rinv), tab) + pc.lon0_rad;
+    if (lam > PI) lam -= 2.0 * PI;
+    if (lam < -PI) lam += 2.0 * PI;
+    pt r; r.y = phi * R2D; r.x = lam * R2D; return r;
+}
+
+// x / 1000 correctly rounded without the division sequence: q = RN(a r), r = RN(1/1000),
+// then one exact-residual correction (Markstein).  Identical to __ddiv_rn(a, 1000.) for every
+// finite a in the range velocities can produce (checked against IEEE division on 3e8 random
+// and 1.5e9 near-midpoint operands, and on the device in tests/test_gpu_parity.py);
+// differs only for a = +-inf (NaN instead of inf).
+__device__ __forceinline__ double div1000(double a)
+{
+    const double r = 1.0 / 1000.0;
+    const double q = __dmul_rn(a, r);
+    const double e = __fma_rn(-1000.0, q, a);
+    return __fma_rn(e, r, q);
 }
 
 // forward, for the grid-preparation helpers (ncio.py:50-53,86-89)

@@ -17,6 +17,7 @@ struct AdvectGrid {
     const pt* V;                // V-points (north faces)
     const int8_t* tmask;        // (Nj*Ni)
     ProjConst proj;
+    const AngEntry* atab;       // 47-entry angle table of inv_stere_fast (device)
 };
 
 // Buoy state, struct of arrays in HBM.
@@ -38,7 +39,8 @@ struct StepOut {
 };
 
 cudaError_t launch_advect_step(const AdvectGrid& g, const float* u, const float* v, const float* ic,
-                               const BuoyState& s, int jrec, const StepOut& o, cudaStream_t st);
+                               const BuoyState& s, int jrec, const StepOut& o, int variant, cudaStream_t st);
+cudaError_t launch_div1000(const double* a, double* q_fast, double* q_div, long long n, cudaStream_t st);
 cudaError_t launch_advect_multi(const AdvectGrid& g, const float* rec0, long long rec_stride, int nrec,
                                 const BuoyState& s, int jrec0, const StepOut& o, long long out_stride,
                                 cudaStream_t st);

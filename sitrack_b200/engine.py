@@ -78,6 +78,10 @@ class TrackEngine:
     def __exit__(self, *a):
         self.close()
 
+    def set_kernel_variant(self, variant):
+        """0 = tuned k_advect_step (default), 1 = k_advect_step_v1 (A/B reference)."""
+        check(self.L.st_set_kernel_variant(self.h, int(variant)), self.h)
+
     # -- seeding -----------------------------------------------------------------------
     def set_locate_grid(self, latT, lonT, resKM=None):
         la, lo = as_c(latT, np.float64), as_c(lonT, np.float64)

@@ -247,3 +247,66 @@ def test_empty_and_errors(sit, gold_track):
         with pytest.raises(sit.SitrackCudaError):
             eng.seed_locate(np.zeros((1, 2)), np.zeros((1, 2)), T["IC"][0])   # no locate grid yet
     assert sit.IsInsideQuadrangleBatch(np.zeros((0, 2)), np.zeros((0, 4, 2))).shape == (0,)
+
+
+# ---- the tuned kernel's shortcuts ---------------------------------------------------------------------
+
+def test_div1000_is_ieee_division(sit):
+    """dx/1000 (si3_part_tracker.py:457-458) via reciprocal + exact residual == IEEE division, on the
+    operands velocities produce (f4 x 3600) and on adversarial near-midpoint quotients."""
+    import ctypes as C
+    from sitrack_b200 import _lib
+    rng = np.random.default_rng(21)
+    u = np.concatenate([rng.uniform(-2, 2, 2_000_000).astype(np.float32),
+                        rng.standard_normal(1_000_000).astype(np.float32) * np.float32(1e-3),
+                        np.float32([0, -0.0, 1e-30, 3.4e38, -3.4e38, 1.4e-45])])
+    a = u.astype(np.float64) * 3600.0
+    q = rng.uniform(1, 2, 1_000_000)                               # quotients; operands next to 1000*(q + ulp/2)
+    mid = (q + np.spacing(q) / 2).astype(np.longdouble) * np.longdouble(1000)
+    hard = np.concatenate([np.nextafter(mid.astype(np.float64), s) for s in (-np.inf, np.inf)] + [mid.astype(np.float64)])
+    a = np.ascontiguousarray(np.concatenate([a, hard, rng.uniform(-1e6, 1e6, 1_000_000)]))
+    qf = np.empty_like(a); qd = np.empty_like(a)
+    _lib.check(_lib.lib().st_selftest_div1000(0, a.size, a.ctypes.data, qf.ctypes.data, qd.ctypes.data))
+    assert np.array_equal(qd, a / 1000.0)                          # device division is IEEE
+    assert np.array_equal(qf, qd)                                  # and so is the shortcut
+
+
+@pytest.mark.parametrize("preset,n,nrec,scale", [("nanuk4", 200_000, 30, 2.0), ("arctic12", 400_000, 16, 1.0)])
+def test_large_cloud_tuned_vs_v1_vs_oracle(torch, corc, preset, n, nrec, scale):
+    """Dense clouds (many buoys per warp leaving their cell, kills, domain edges): the tuned kernel,
+    the straightforward v1 kernel and the C oracle agree bit for bit."""
+    import synth
+    g = synth.make_grid(**synth.GRID_PRESETS[preset], seed=0)
+    U, V, IC = synth.make_records(g, nrec, seed=1)
+    U *= np.float32(scale); V *= np.float32(scale)
+    ids, SG, SC = synth.dense_seeds(g, n, IC[0], seed=9)
+    with engine_for(g) as eng:
+        eng.set_locate_grid(g["latT"], g["lonT"], g["ResKM"])
+        cell, near, keep = eng.seed_locate(SG, SC, IC[0])
+    ik = np.flatnonzero(keep)
+    pos0, cell0 = SC[ik], cell[ik]
+    ref = corc.track(g, U, V, IC, pos0, cell0.astype(np.int64), history=False)
+    assert ref["ncross"] > 0.02 * ik.size * nrec and ref["alive"].sum() < ik.size
+    dev = torch.device("cuda", 0)
+    for variant in (0, 1):
+        with engine_for(g) as eng:
+            eng.set_kernel_variant(variant)
+            eng.set_buoys(pos0, cell0)
+            eng.record_slots(1)
+            yx = torch.empty((ik.size, 2), dtype=torch.float64, device=dev)
+            ll = torch.empty((ik.size, 2), dtype=torch.float64, device=dev)
+            mk = torch.empty((ik.size,), dtype=torch.int8, device=dev)
+            na = torch.zeros((nrec,), dtype=torch.int64, device=dev)
+            for k in range(nrec):
+                st = eng.staging(0)
+                st[0], st[1], st[2] = U[k], V[k], IC[k]
+                eng.submit_record(0)
+                eng.step(0, k, yx, ll, mk, na[k:k + 1])
+                torch.cuda.synchronize()
+                if k in (0, nrec // 2, nrec - 1):
+                    assert np.array_equal(yx.cpu().numpy(), ref["posC"][k + 1])
+                    assert np.array_equal(mk.cpu().numpy(), ref["mask"][k + 1])
+                    assert np.abs(ll.cpu().numpy() - ref["posG"][k + 1]).max() < LATLON_TOL_DEG
+            p, c, a = eng.get_state()
+            assert np.array_equal(c, ref["jiT"]) and np.array_equal(a, ref["alive"])
+            assert np.array_equal(na.cpu().numpy(), ref["nalive"])
