@@ -165,7 +165,7 @@ def run_ours(args):
     R = U.shape[0]
     eng = sit.TrackEngine(g["Yf"], g["Xf"], g["Yu"], g["Xu"], g["Yv"], g["Xv"], tmask=g["tmask"], device=local)
     launches = {"n": 0}
-    eng.set_kernel_variant(1 if args.kernel == "v1" else 0)
+    eng.set_kernel_variant({"tuned": 0, "v1": 1}.get(args.kernel, None) if args.kernel in ("tuned", "v1") else int(args.kernel))
 
     # -- seeding on the device (k_seed_locate), timed separately ------------------------------
     eng.set_locate_grid(g["latT"], g["lonT"], g["ResKM"])
@@ -258,7 +258,7 @@ def run_ours(args):
     # roofline of the dominant kernel on THIS rank: algorithmic bytes / its mean launch duration.
     # The K launches run back to back on one stream, so the event span / K is the launch duration.
     achieved = (bsteps / K) * B_ALG / (ms / K * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_advect_step<1,false>" if args.kernel == "tuned" else "k_advect_step_v1<1,false>", "achieved": round(achieved, 1), "peak": peak,
+    roof = {"bound": "hbm", "kernel": "k_advect_step_v1<1,false>" if args.kernel == "v1" else "k_advect_step<1,false> (%s)" % args.kernel, "achieved": round(achieved, 1), "peak": peak,
             "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload),
             "peak_source": peak_src, "alg_bytes_per_buoy_step": B_ALG,
             "buoy_steps_per_launch": bsteps / K, "us_per_launch": round(ms / K * 1e3, 2)}
@@ -529,7 +529,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=list(WORKLOADS))
-    ap.add_argument("--kernel", default="tuned", choices=["tuned", "v1"], help="k_advect_step variant (A/B)")
+    ap.add_argument("--kernel", default="tuned", help="k_advect_step variant: tuned, v1, or an integer launch-bound experiment")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--no-allgather", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -1,0 +1,221 @@
+#!/usr/bin/env python3
+"""SITRACK ice particle tracker -- B200 drop-in for the reference's `si3_part_tracker.py`.
+
+Same command line (-i -m -s required; -k -e -F -N -p), same file-name conventions, same
+seeding cache (`./seed/Initialized_buoys_<Seed>_<CONF>.npz`) and the same two output files
+(`./nc/..._tracking_...` with -F, and the 2-record `..._tracking12_...`), but the seeding
+loop (reference tracking.py:120-160) and the records x buoys loop
+(reference si3_part_tracker.py:361-496) run on the GPU through sitrack_b200.TrackEngine.
+Inputs may be netCDF (needs netCDF4) or the `.npz` equivalents described in
+sitrack_b200/ncio.py.  Plotting (-p) is accepted and ignored: the plotting stack (mojito,
+cartopy) is outside the scope of this path.
+"""
+from os import path, makedirs
+from re import split
+from sys import exit
+
+import numpy as np
+
+import sitrack_b200 as sit
+from sitrack_b200 import epoch2clock as e2c
+
+idebug = 0
+rdt = 3600.          # time step [s] of the model output used (reference :31)
+iUVstrategy = 1      # 0: mean of the two faces, 1: nearest U / nearest V point (reference :37)
+
+
+def __argument_parsing__():
+    import argparse as ap
+    parser = ap.ArgumentParser(description='SITRACK ICE PARTICULES TRACKER')
+    rq = parser.add_argument_group('required arguments')
+    rq.add_argument('-i', '--fsi3', required=True, help='output file of SI3 containing ice velocities ans co')
+    rq.add_argument('-m', '--fmmm', required=True, help='model `mesh_mask` file of NEMO config used in SI3 run')
+    rq.add_argument('-s', '--fsdg', required=True, help='seeding file')
+    parser.add_argument('-k', '--krec', type=int, default=0, help='record of seeding file to use to seed from')
+    parser.add_argument('-e', '--dend', default=None, help='date at which to stop')
+    parser.add_argument('-F', '--fxdt', action="store_true", help='fixed tracking time (1D time array)')
+    parser.add_argument('-N', '--ncnf', default='NANUK4', help='name of the horizontak NEMO config used')
+    parser.add_argument('-p', '--plot', type=int, default=0, help='(ignored) how often we plot the positions on a map')
+    parser.add_argument('--device', type=int, default=None, help='CUDA device (default: LOCAL_RANK or 0)')
+    parser.add_argument('--uvstrategy', type=int, default=iUVstrategy, choices=[0, 1])
+    args = parser.parse_args()
+    print('')
+    print(' *** SI3 file to get ice velocities from => ', args.fsi3)
+    print(' *** SI3 `mesh_mask` metrics file        => ', args.fmmm)
+    print(' *** Seeding file and record to use      => ', args.fsdg, args.krec)
+    if args.dend:
+        print(' *** Overidding date at which to stop =>', args.dend)
+    if args.ncnf:
+        print(' *** Name of the horizontak NEMO config used => ', args.ncnf)
+    return args
+
+
+def seed_name_info(fNCseedBN):
+    """`csfkm`, `cdtbin` from the seeding file name (reference :115-148)."""
+    csfkm = ''
+    stem = split(r'\.', fNCseedBN)[0]
+    parts = split('_', stem)
+    if parts[2] in ['nemoTsi3', 'nemoTmm', 'sidfex']:
+        print('\n *** Seems to be an idealized seeding of type "' + parts[2] + '"')
+        cdtbin = '_idlSeed'
+        for ii in [1, 2, 3]:
+            ckm = '_' + parts[-ii]
+            if ckm[-2:] == 'km':
+                csfkm = ckm
+                break
+    else:
+        lok, itst = False, 1
+        base = split('_', split(r'\.', fNCseedBN)[-2])
+        while not lok:
+            itst -= 1
+            csfkm = '_' + base[itst]
+            cdtbin = '_' + base[-3 + itst]
+            lok = (csfkm[-2:] == 'km' and cdtbin[1:3] == 'dt') or (cdtbin[1:3] == 'dt' and itst == 0)
+            if itst < -4:
+                print('ERROR: we could not figure out `csfkm` and `cdtbin` from file name!', csfkm, cdtbin)
+                exit(0)
+        if itst == 0:
+            csfkm = ''
+    return csfkm, cdtbin
+
+
+def record_windows(zTpos, nP, kstrt, kstop, ztime_model, iTmA, iTmB):
+    """First/last model record per buoy without -F (reference :264-312)."""
+    z1st = np.zeros(nP, dtype=int) + kstrt
+    zLst = np.zeros(nP, dtype=int) + kstop
+    (n2, nB) = np.shape(zTpos)
+    if n2 != 2 or nP != nB:
+        print('ERROR: wrong shape for the 2D time array `zTpos`! `n2,nB`, vs `nP`:', n2, nB, nP)
+        exit(0)
+    half = int(rdt / 2)
+    for jb in np.where(zTpos[0, :] >= iTmA + half)[0]:
+        (idx,) = np.where(ztime_model + half < zTpos[0, jb])
+        z1st[jb] = idx[-1] + 1
+    for jb in np.where(zTpos[1, :] < iTmB - half)[0]:
+        (idx,) = np.where(ztime_model - half > zTpos[1, jb])
+        zLst[jb] = idx[0] - 1
+    return z1st, zLst
+
+
+def main():
+    print('\n##########################################################')
+    print('#            SITRACK ICE PARTICULES TRACKER              #')
+    print('#                 (sitrack_b200 engine)                  #')
+    print('##########################################################\n')
+    args = __argument_parsing__()
+    cf_uv, cf_mm, fNCseed, jrecSeed, cdate_stop, CONF = args.fsi3, args.fmmm, args.fsdg, args.krec, args.dend, args.ncnf
+    lUse2DTime = not args.fxdt
+    if args.device is not None:
+        sit.config.device = args.device
+    if args.plot:
+        print(' *** NOTE: -p/--plot is accepted but plotting is not part of sitrack_b200; ignoring.')
+    fNCseedBN = path.basename(fNCseed)
+    csfkm, cdtbin = seed_name_info(fNCseedBN)
+    creskm = csfkm[1:] if csfkm != '' else ''
+
+    idateSeedA, idateSeedB, SeedName, SeedBatch, zTpos = sit.SeedFileTimeInfo(fNCseed, ltime2d=lUse2DTime, iverbose=idebug)
+    Nt0, ztime_model, idateModA, idateModB, ModConf, ModExp = sit.ModelFileTimeInfo(cf_uv, iverbose=idebug)
+
+    date_stop = None
+    if cdate_stop:
+        date_stop = sit.clock2epoch(cdate_stop) if len(cdate_stop) == 19 else sit.clock2epoch(cdate_stop, precision='D', cfrmt='guess')
+    elif idateSeedB - idateSeedA >= 3600.:
+        date_stop = idateSeedB
+    Nt, kstrt, kstop, iTmA, iTmB = sit.GetTimeSpan(rdt, ztime_model, idateSeedA, idateModA, idateModB, iStop=date_stop)
+    if Nt < 1:
+        print(' QUITTING since no matching model records!')
+        exit(0)
+    for cd in ['seed', 'nc', 'npz']:
+        makedirs(cd, exist_ok=True)
+
+    imaskt, xlatT, xlonT, xYt, xXt, xYf, xXf, xResKM = sit.GetModelGrid(cf_mm)
+    xYv, xXv, xYu, xXu = sit.GetModelUVGrid(cf_mm) if args.uvstrategy == 1 else (None, None, None, None)
+    (Nj, Ni) = np.shape(imaskt)
+
+    ds = sit.open_dataset(cf_uv)
+    vU, vV, vIC = ds.variables['u_ice'], ds.variables['v_ice'], ds.variables['siconc']
+
+    # ---- initialization / seeding (reference :205-255) ----------------------------------------
+    cf_npz_itm = './seed/Initialized_buoys_' + SeedName + '_' + CONF + '.npz'
+    if path.exists(cf_npz_itm):
+        print('\n *** We found file ' + cf_npz_itm + ' here! So using it and skipping first stage!')
+        with np.load(cf_npz_itm) as data:
+            nP = int(data['nP']); xPosG0 = data['xPosG0']; xPosC0 = data['xPosC0']; IDs = data['IDs']
+            vJIt = data['vJIt']; VRTCS = data['VRTCS']; idxK = data['idxKeep']
+    else:
+        print('\n *** We did not find file ' + cf_npz_itm + ' ! => locating the seeds on the GPU...')
+        xIC0 = np.asarray(vIC[kstrt, :, :], dtype=np.float32)
+        zt, zIDs, XseedG, XseedC = sit.LoadNCdata(fNCseed, krec=jrecSeed, iverbose=idebug)
+        print('     => data used for seeding is read at date =', e2c(zt), '\n        (shape of XseedG =', np.shape(XseedG), ')')
+        (nP, _) = np.shape(XseedG)
+        IDs = np.array(zIDs, dtype=int)
+        nPn, xPosG0, xPosC0, IDs, vJIt, VRTCS, idxK = sit.SeedInit(IDs, XseedG, XseedC, xlatT, xlonT, xYf, xXf,
+                                                                   xResKM, imaskt, xIceConc=xIC0, iverbose=idebug)
+        if nPn < nP:
+            print('\n *** `SeedInit()` had to cancel ' + str(nP - nPn) + ' buoys! => updating nP from ' + str(nP) + ' to ' + str(nPn) + '!')
+            nP = nPn
+        print('\n *** Saving intermediate data into ' + cf_npz_itm + '!')
+        np.savez_compressed(cf_npz_itm, nP=nP, xPosG0=xPosG0, xPosC0=xPosC0, IDs=IDs, vJIt=vJIt, VRTCS=VRTCS, idxKeep=idxK)
+
+    z1st = zLst = None
+    if lUse2DTime:
+        z1st, zLst = record_windows(zTpos, nP, kstrt, kstop, ztime_model, iTmA, iTmB)
+
+    # ---- the record loop on the GPU (reference :361-496) -----------------------------------------
+    vTime = np.zeros(Nt + 1, dtype=int)
+    for jt in range(Nt):
+        vTime[jt] = int(ztime_model[jt + kstrt]) - int(rdt / 2.)
+    vTime[Nt] = vTime[Nt - 1] + int(rdt)
+
+    def record(k):
+        jrec = k + kstrt
+        print('\n *** Reading record #' + str(jrec + 1) + '/' + str(Nt0) + ' in SI3 file ==> date =', e2c(vTime[k]),
+              '(model:' + e2c(int(ztime_model[jrec])) + ')')
+        return vU[jrec, :, :], vV[jrec, :, :], vIC[jrec, :, :]
+
+    eng = sit.TrackEngine(xYf, xXf, xYu, xXu, xYv, xXv, tmask=imaskt, uv_strategy=args.uvstrategy, rdt=rdt,
+                          rmin_conc=sit.rmin_conc, device=sit.config.device)
+    eng.set_buoys(xPosC0, vJIt, z1st, zLst)
+    res = eng.track(record, Nt, kstrt=kstrt, pos0=xPosC0, posG0=xPosG0, rec_first=z1st)
+    eng.close()
+    ds.close()
+    xPosC, xPosG, xmask = res['posC'], res['posG'], res['mask']
+    for jt in range(Nt):
+        print('   *   record ' + str(jt + kstrt) + ': number of buoys alive = ' + str(int(res['n_alive'][jt])))
+
+    # ---- outputs (reference :498-571) ---------------------------------------------------------------
+    def hstr(it):
+        c = split(':', e2c(it))[0]
+        return c.replace('-', '').replace('_', 'h')
+    corgn = 'NEMO-SI3_' + ModConf + '_' + ModExp
+    ext = '.npz' if str(cf_uv).endswith('.npz') else '.nc'
+    if not lUse2DTime:
+        cf_nc_out = './nc/' + corgn + '_tracking_' + SeedBatch + cdtbin + '_' + hstr(vTime[0]) + '_' + hstr(vTime[Nt]) + csfkm + ext
+        sit.ncSaveCloudBuoys(cf_nc_out, vTime, IDs, xPosC[:, :, 0], xPosC[:, :, 1], xPosG[:, :, 0], xPosG[:, :, 1],
+                             mask=xmask, corigin=corgn)
+    z2XY, z2GC, zMSK = np.zeros((2, nP, 2)), np.zeros((2, nP, 2)), np.zeros((2, nP), dtype='i1')
+    if lUse2DTime:
+        # per-buoy first and last valid rows; xTime follows from the windows (reference :334-340, :463)
+        zTim = np.zeros((2, nP), dtype=int)
+        for jb in range(nP):
+            k0 = z1st[jb] - kstrt
+            kN = zLst[jb] - kstrt + 1
+            z2XY[0, jb], z2GC[0, jb], zMSK[0, jb] = xPosC[k0, jb], xPosG[k0, jb], xmask[k0, jb]
+            z2XY[1, jb], z2GC[1, jb], zMSK[1, jb] = xPosC[kN, jb], xPosG[kN, jb], xmask[kN, jb]
+            zTim[0, jb] = ztime_model[z1st[jb]] - int(rdt / 2)
+            zTim[1, jb] = (vTime[kN - 1] + int(rdt)) if xmask[kN, jb] else sit.FillValue
+        zvt = np.array([np.mean(zTim[0, :]), np.mean(zTim[1, :])])
+    else:
+        z2XY[0], z2GC[0], zMSK[0] = xPosC[0], xPosG[0], xmask[0]
+        z2XY[1], z2GC[1], zMSK[1] = xPosC[Nt], xPosG[Nt], xmask[Nt]
+        zTim = []
+        zvt = np.array([vTime[0], vTime[Nt]])
+    cf_nc_out = './nc/' + corgn + '_tracking12_' + SeedBatch + cdtbin + '_' + hstr(zvt[0]) + '_' + hstr(zvt[1]) + csfkm + ext
+    sit.ncSaveCloudBuoys(cf_nc_out, zvt, IDs, z2XY[:, :, 0], z2XY[:, :, 1], z2GC[:, :, 0], z2GC[:, :, 1],
+                         mask=zMSK, xtime=zTim, corigin=corgn)
+    print('        => global first and final dates in simulated trajectories:', e2c(zvt[0]), e2c(zvt[1]), '\n')
+    return 0
+
+
+if __name__ == '__main__':
+    main()

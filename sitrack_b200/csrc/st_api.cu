@@ -201,7 +201,7 @@ int st_create(st_ctx** out, int device, int Nj, int Ni, const double* Yf, const 
 
 int st_set_kernel_variant(st_ctx* c, int variant)
 {
-    if (!c || variant < 0 || variant > 1) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 (tuned) or 1 (v1)");
+    if (!c || variant < 0 || variant > 8) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 (tuned), 1 (v1), 2..7 (launch-bound experiments), 8 (pipelined)");
     c->variant = variant;
     return ST_OK;
 }
@@ -365,10 +365,15 @@ static int reserve_buoys(st_ctx* c, int64_t nP, bool window)
     if (nP > c->capP) {
         cudaFree(c->pos); cudaFree(c->cell); cudaFree(c->alive); cudaFree(c->rec_first); cudaFree(c->rec_last);
         c->pos = nullptr; c->cell = nullptr; c->alive = nullptr; c->rec_first = c->rec_last = nullptr; c->capP = 0;
-        CU(c, cudaMalloc(&c->pos, sizeof(pt) * nP));
-        CU(c, cudaMalloc(&c->cell, sizeof(int2) * nP));
-        CU(c, cudaMalloc(&c->alive, (size_t)nP));
-        c->capP = nP;
+        // capacity padded to whole 256-buoy tiles: k_advect_pipe moves state with fixed-size TMA bulk copies
+        const long long cap = ((nP + 255) / 256) * 256;
+        CU(c, cudaMalloc(&c->pos, sizeof(pt) * cap));
+        CU(c, cudaMalloc(&c->cell, sizeof(int2) * cap));
+        CU(c, cudaMalloc(&c->alive, (size_t)cap));
+        CU(c, cudaMemset(c->pos, 0, sizeof(pt) * cap));
+        CU(c, cudaMemset(c->cell, 0, sizeof(int2) * cap));
+        CU(c, cudaMemset(c->alive, 0, (size_t)cap));
+        c->capP = cap;
     }
     if (window && !c->rec_first) {
         CU(c, cudaMalloc(&c->rec_first, sizeof(int32_t) * c->capP));

@@ -1,0 +1,85 @@
+"""The drop-in command line: CPU test of the file-name / time-axis plumbing and the npz I/O
+backend, GPU test of a full `si3_part_tracker.py -F` run against the C oracle."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def test_seed_name_parsing():
+    import si3_part_tracker as cli
+    assert quiet(cli.seed_name_info, "sitrack_seeding_nemoTsi3_19961215_00_HSS5.nc") == ("", "_idlSeed")
+    assert quiet(cli.seed_name_info, "sitrack_seeding_sidfex_19961215_00_10km.nc") == ("_10km", "_idlSeed")
+    assert quiet(cli.seed_name_info, "SELECTION_RGPS_S000_dt72_19970104h00_19970107h00_20km.nc") == ("_20km", "_dt72")
+
+
+def test_npz_io_roundtrip(tmp_path):
+    import sitrack_b200 as sit
+    from make_synth_case import write_case
+    r = write_case(str(tmp_path), grid="tiny", nrec=6, hss=2)
+    Nt, t, d0, dN, conf, exp = quiet(sit.ModelFileTimeInfo, r["si3"])
+    assert (Nt, conf, exp) == (6, "SYNTH4", "SYN00") and t.dtype == np.int32
+    a, b, name, batch, t2 = quiet(sit.SeedFileTimeInfo, r["seed"])
+    assert (a, b, batch) == (850608000, 850608000, "nemoTsi3") and name == "sitrack_seeding_nemoTsi3_19961215_00_HSS2"
+    zt, ids, LL, YX = quiet(sit.LoadNCdata, r["seed"], krec=0)
+    assert LL.shape == YX.shape == (ids.size, 2) and LL.dtype == np.float64 and (LL[:, 1] >= 0).all()
+    # writer: same variables and dtypes as ncSaveCloudBuoys (ncio.py:131-197)
+    f = str(tmp_path / "out.npz")
+    quiet(sit.ncSaveCloudBuoys, f, np.array([1, 2]), ids, np.tile(YX[:, 0], (2, 1)), np.tile(YX[:, 1], (2, 1)),
+          np.tile(LL[:, 0], (2, 1)), np.tile(LL[:, 1], (2, 1)), mask=np.ones((2, ids.size), "i1"))
+    z = np.load(f)
+    assert z["time"].dtype == np.int32 and z["id_buoy"].dtype == np.int64 and z["y_pos"].dtype == np.float32
+    assert z["mask"].dtype == np.int8 and z["latitude"].shape == (2, ids.size)
+    zt2, ids2, LL2, YX2, msk = quiet(sit.LoadNCdata, f, krec=1, lmask=True)
+    assert np.array_equal(ids2, ids) and np.array_equal(YX2, YX)            # f4 values survive the round trip
+
+
+@pytest.mark.gpu
+def test_cli_full_run_vs_oracle(tmp_path, monkeypatch):
+    import si3_part_tracker as cli
+    from make_synth_case import write_case
+    from oracle import corc
+    import sitrack_b200 as sit
+    r = write_case(str(tmp_path / "in"), grid="small", nrec=24, hss=3)
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(sys, "argv", ["si3_part_tracker.py", "-i", r["si3"], "-m", r["mesh"], "-s", r["seed"],
+                                      "-F", "-N", "SYNTH4"])
+    quiet(cli.main)
+    out = [f for f in os.listdir(tmp_path / "nc") if "_tracking_" in f]
+    out12 = [f for f in os.listdir(tmp_path / "nc") if "_tracking12_" in f]
+    assert out == ["NEMO-SI3_SYNTH4_SYN00_tracking_nemoTsi3_idlSeed_19961215h00_19961216h00.npz"], out
+    assert len(out12) == 1
+    z = np.load(tmp_path / "nc" / out[0])
+    cache = np.load(tmp_path / "seed" / "Initialized_buoys_sitrack_seeding_nemoTsi3_19961215_00_HSS3_SYNTH4.npz")
+    assert sorted(cache.files) == sorted(["nP", "xPosG0", "xPosC0", "IDs", "vJIt", "VRTCS", "idxKeep"])
+    # the same run through the oracle, from the grid the CLI derived (device forward projection of lat/lon)
+    kmaskt, latT, lonT, Yt, Xt, Yf, Xf, ResKM = quiet(sit.GetModelGrid, r["mesh"])
+    Yv, Xv, Yu, Xu = quiet(sit.GetModelUVGrid, r["mesh"])
+    g0 = r["grid"]
+    assert np.abs(Yf - g0["Yf"]).max() < 1e-6 and np.abs(Xu - g0["Xu"]).max() < 1e-6       # km, projection round trip
+    g = dict(Yf=Yf, Xf=Xf, Yu=Yu, Xu=Xu, Yv=Yv, Xv=Xv, tmask=kmaskt)
+    U, V, IC = r["records"]
+    ref = corc.track(g, U, V, IC, cache["xPosC0"], cache["vJIt"].astype(np.int64))
+    assert z["time"].shape == (25,) and z["y_pos"].shape == (25, int(cache["nP"]))
+    assert np.array_equal(z["mask"], ref["mask"])
+    assert np.array_equal(z["y_pos"], ref["posC"][:, :, 0].astype("f4"))                  # file dtype is f4
+    assert np.array_equal(z["x_pos"], ref["posC"][:, :, 1].astype("f4"))
+    lat_ref = corc.inv_stere(ref["posC"][1:].reshape(-1, 2)).reshape(24, -1, 2)
+    assert np.abs(z["latitude"][1:] - lat_ref[:, :, 0].astype("f4")).max() <= 8e-6        # <= 1 ulp(f4) at 90 deg
+    z12 = np.load(tmp_path / "nc" / out12[0])
+    assert np.array_equal(z12["y_pos"][1], z["y_pos"][-1]) and z12["time"].tolist() == [int(z["time"][0]), int(z["time"][-1])]
+    # second run hits the seeding cache and gives the same file
+    quiet(cli.main)
+    z2 = np.load(tmp_path / "nc" / out[0])
+    assert np.array_equal(z2["y_pos"], z["y_pos"])

@@ -74,11 +74,13 @@ def test_haversine_golden(sit, gold_pred):
 
 # ---- the record loop against the reference's golden trajectories ----------------------------
 
-def _run_engine(torch, g, U, V, IC, pos0, cell0, kstrt=0, first=None, last=None, uv_strategy=1, multi=False):
+def _run_engine(torch, g, U, V, IC, pos0, cell0, kstrt=0, first=None, last=None, uv_strategy=1, multi=False,
+                variant=0):
     nrec = U.shape[0]
     nP = pos0.shape[0]
     dev = torch.device("cuda", 0)
     with engine_for(g, uv_strategy=uv_strategy) as eng:
+        eng.set_kernel_variant(variant)
         eng.set_buoys(pos0, cell0, first, last)
         yx = torch.empty((nrec, nP, 2), dtype=torch.float64, device=dev)
         ll = torch.empty((nrec, nP, 2), dtype=torch.float64, device=dev)
@@ -125,6 +127,23 @@ def test_track_golden(torch, corc, gold_track, name, multi):
         assert np.array_equal(alive, T[name + "_alive"])
     want = corc.inv_stere(T[name + "_posC"][1:].reshape(-1, 2)).reshape(ll.shape)
     assert np.abs(ll - want).max() < LATLON_TOL_DEG                  # also for the -9999 rows (:493)
+
+
+@pytest.mark.parametrize("variant", [1, 5, 8])
+@pytest.mark.parametrize("name", list(TRACK_CASES))
+def test_track_golden_other_kernels(torch, gold_track, name, variant):
+    """v1 (straightforward), a 128-thread launch-bound variant and the persistent TMA/cp.async
+    pipelined kernel reproduce the reference's golden trajectories bit for bit too."""
+    T, g = gold_track
+    c = TRACK_CASES[name]
+    s = np.float32(c["scale"])
+    first = T["win_first"] if c["win"] else None
+    last = T["win_last"] if c["win"] else None
+    yx, ll, mk, na, cells, alive = _run_engine(torch, g, s * T["U"], s * T["V"], T["IC"], T["pos0"], T["jiT0"],
+                                               c["kstrt"], first, last, c["uv_strategy"], False, variant)
+    assert np.array_equal(yx, T[name + "_posC"][1:]) and np.array_equal(mk, T[name + "_mask"][1:])
+    assert np.array_equal(na, T[name + "_nalive"])
+    assert np.array_equal(cells, T[name + "_jiT"]) and np.array_equal(alive, T[name + "_alive"])
 
 
 def test_track_host_call_and_pipeline(torch, gold_track):
@@ -288,7 +307,7 @@ def test_large_cloud_tuned_vs_v1_vs_oracle(torch, corc, preset, n, nrec, scale):
     ref = corc.track(g, U, V, IC, pos0, cell0.astype(np.int64), history=False)
     assert ref["ncross"] > 0.02 * ik.size * nrec and ref["alive"].sum() < ik.size
     dev = torch.device("cuda", 0)
-    for variant in (0, 1):
+    for variant in (0, 1, 8):
         with engine_for(g) as eng:
             eng.set_kernel_variant(variant)
             eng.set_buoys(pos0, cell0)
