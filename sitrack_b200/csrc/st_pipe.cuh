@@ -217,12 +217,7 @@ k_advect_pipe(const AdvectGrid g, const float* __restrict__ u, const float* __re
         asm volatile("cp.async.commit_group;" ::: "memory");
         // ---- inside test, rows, state ----------------------------------------------------------
         if (act) {
-            const double y = outp.y, x = outp.x;
-            const bool g0 = y > bl.y, g1 = y > br.y, g2 = y > ur.y, g3 = y > ul.y;
-            const bool l0 = x <= bl.x, l1 = x <= br.x, l2 = x <= ur.x, l3 = x <= ul.x;
-            const bool in = edge_toggles2(y, x, bl, br, g0, g1, l0, l1) ^ edge_toggles2(y, x, br, ur, g1, g2, l1, l2) ^
-                            edge_toggles2(y, x, ur, ul, g2, g3, l2, l3) ^ edge_toggles2(y, x, ul, bl, g3, g0, l3, l0);
-            cross = !in;
+            cross = !inside_quad2(outp.y, outp.x, bl, br, ur, ul);
             st_stream_pt(s.pos + p, outp);
         }
         if (valid) {
