@@ -143,7 +143,7 @@ def seed_init(SG, SC, latT, lonT, Yf, Xf, reskm, tmask, ic0, rmin_conc=0.1):
 
 
 def track(grid, U, V, IC, pos0, jiT0, kstrt=0, rec_first=None, rec_last=None, uv_strategy=1,
-          rdt=3600.0, rmin_conc=0.1, do_latlon=True, history=True, posG0=None):
+          rdt=3600.0, rmin_conc=0.1, do_latlon=True, history=True, posG0=None, alive0=None):
     """Run the record x buoy loop.  grid: dict with Yf,Xf,Yu,Xu,Yv,Xv (f8) and tmask (i1).
     U,V,IC: (nrec,Nj,Ni) f4.  pos0 (nP,2) [y,x] km, jiT0 (nP,2).  -F semantics unless
     rec_first/rec_last are given (then row k0 = rec_first-kstrt holds the seed)."""
@@ -166,7 +166,7 @@ def track(grid, U, V, IC, pos0, jiT0, kstrt=0, rec_first=None, rec_last=None, uv
             if posG0 is not None:
                 posG[k0, b] = posG0[b]
     jiT = _c(jiT0, "i8").copy()
-    alive = np.ones(nP, np.int8)
+    alive = np.ones(nP, np.int8) if alive0 is None else _c(alive0, "i1").copy()
     nal = np.zeros(nrec, np.int64)
     jh = np.zeros((nrec + 1, nP, 2), np.int32) if history else None
     ah = np.zeros((nrec + 1, nP), np.int8) if history else None

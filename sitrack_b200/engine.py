@@ -221,6 +221,8 @@ class TrackEngine:
         dev = torch.device("cuda", self.device)
         nP = self.nP
         get = _record_getter(records)
+        if chunk and chunk > 1 and sink is None:
+            return self._track_chunked(get, nrec, kstrt, pos0, posG0, rec_first, want_latlon, int(chunk))
         self.record_slots(2)
         stg = [self.staging(0), self.staging(1)]
         s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
@@ -298,6 +300,76 @@ class TrackEngine:
                         if posG0 is not None:
                             posG[0, b] = posG0[b]
         return dict(posC=posC, posG=posG, mask=mask, n_alive=n_alive)
+
+
+def _finish_rows(posC, posG, mask, pos0, posG0, rec_first, kstrt):
+    """Row 0 of the series is the seed (si3_part_tracker.py:335-344)."""
+    if pos0 is None:
+        return
+    if rec_first is None:
+        posC[0] = pos0; mask[0] = 1
+        if posG0 is not None:
+            posG[0] = posG0
+    else:
+        k0 = np.asarray(rec_first) - kstrt
+        sel = np.flatnonzero(k0 == 0)
+        posC[0, sel] = np.asarray(pos0)[sel]; mask[0, sel] = 1
+        if posG0 is not None:
+            posG[0, sel] = np.asarray(posG0)[sel]
+
+
+def _track_chunked(self, get, nrec, kstrt, pos0, posG0, rec_first, want_latlon, chunk):
+    """Season path for small clouds: `chunk` records at a time are staged into HBM and advanced by
+    ONE launch of k_advect_multi (each thread runs its buoy through the whole chunk), instead of
+    one launch per record.  Host fill of chunk c+1 || H2D || compute of chunk c || D2H of its rows."""
+    torch = _torch()
+    dev = torch.device("cuda", self.device)
+    nP, Nj, Ni = self.nP, self.Nj, self.Ni
+    s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    h_rec = [torch.empty((chunk, 3, Nj, Ni), dtype=torch.float32).pin_memory() for _ in range(2)]
+    d_rec = [torch.empty((chunk, 3, Nj, Ni), dtype=torch.float32, device=dev) for _ in range(2)]
+    d_yx = [torch.empty((chunk, nP, 2), dtype=torch.float64, device=dev) for _ in range(2)]
+    d_ll = [torch.empty((chunk, nP, 2), dtype=torch.float64, device=dev) for _ in range(2)] if want_latlon else [None, None]
+    d_mk = [torch.empty((chunk, nP), dtype=torch.int8, device=dev) for _ in range(2)]
+    d_na = torch.zeros((nrec,), dtype=torch.int64, device=dev)
+    posC = torch.full((nrec + 1, nP, 2), FillValue, dtype=torch.float64).pin_memory()
+    posG = torch.full((nrec + 1, nP, 2), FillValue, dtype=torch.float64).pin_memory()
+    mask = torch.zeros((nrec + 1, nP), dtype=torch.int8).pin_memory()
+    nch = (nrec + chunk - 1) // chunk
+    ev_in, ev_cmp, ev_out = [None] * nch, [None] * nch, [None] * nch
+    for c in range(nch):
+        b = c % 2
+        k0, n = c * chunk, min(chunk, nrec - c * chunk)
+        if c >= 2:
+            ev_in[c - 2].synchronize()                      # pinned stack b has left the host
+        hv = h_rec[b].numpy()
+        for k in range(n):
+            u, v, ic = get(k0 + k)
+            hv[k, 0], hv[k, 1], hv[k, 2] = u, v, ic
+        if c >= 2:
+            s_in.wait_event(ev_cmp[c - 2])                  # device stack b no longer read
+        with torch.cuda.stream(s_in):
+            d_rec[b][:n].copy_(h_rec[b][:n], non_blocking=True)
+        ev_in[c] = torch.cuda.Event(); ev_in[c].record(s_in)
+        s_cmp.wait_event(ev_in[c])
+        if c >= 2:
+            s_cmp.wait_event(ev_out[c - 2])                 # row buffers b drained
+        self.step_multi(d_rec[b][:n], k0 + kstrt, d_yx[b], d_ll[b], d_mk[b], d_na[k0:k0 + n], s_cmp)
+        ev_cmp[c] = torch.cuda.Event(); ev_cmp[c].record(s_cmp)
+        s_out.wait_event(ev_cmp[c])
+        with torch.cuda.stream(s_out):
+            posC[k0 + 1:k0 + 1 + n].copy_(d_yx[b][:n], non_blocking=True)
+            if want_latlon:
+                posG[k0 + 1:k0 + 1 + n].copy_(d_ll[b][:n], non_blocking=True)
+            mask[k0 + 1:k0 + 1 + n].copy_(d_mk[b][:n], non_blocking=True)
+        ev_out[c] = torch.cuda.Event(); ev_out[c].record(s_out)
+    torch.cuda.synchronize(dev)
+    posC, posG, mask = posC.numpy(), posG.numpy(), mask.numpy()
+    _finish_rows(posC, posG, mask, pos0, posG0, rec_first, kstrt)
+    return dict(posC=posC, posG=posG, mask=mask, n_alive=d_na.cpu().numpy())
+
+
+TrackEngine._track_chunked = _track_chunked
 
 
 def _record_getter(records):

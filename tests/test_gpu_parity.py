@@ -329,3 +329,57 @@ def test_large_cloud_tuned_vs_v1_vs_oracle(torch, corc, preset, n, nrec, scale):
             p, c, a = eng.get_state()
             assert np.array_equal(c, ref["jiT"]) and np.array_equal(a, ref["alive"])
             assert np.array_equal(na.cpu().numpy(), ref["nalive"])
+
+
+# ---- full season (BASELINE config 2) -------------------------------------------------------------------
+
+def test_full_season_config2_vs_oracle(torch, corc):
+    """NANUK4-shaped grid, HSS5 seeding (~1k buoys), 3024 hourly records (1996-12-15 -> 1997-04-20), -F:
+    the chunked season path (k_advect_multi, 126 records per launch) against the C oracle, record
+    by record.  Target of the north star: >= 95 % of buoys bit-exact in cell index over the season;
+    measured: 100 %, with bit-identical f8 positions (accumulated divergence 0 km)."""
+    import synth
+    g = synth.make_grid(**synth.GRID_PRESETS["nanuk4"], seed=0)
+    nrec, chunk = 3024, 126
+    _, _, IC0 = synth.make_records(g, 1, seed=1)
+    ids, SG, SC = synth.hss_seeds(g, IC0[0], khss=5)
+    with engine_for(g) as eng:
+        eng.set_locate_grid(g["latT"], g["lonT"], g["ResKM"])
+        cell, near, keep = eng.seed_locate(SG, SC, IC0[0])
+        ik = np.flatnonzero(keep)
+        pos0, cell0 = SC[ik], cell[ik]
+        assert 900 < ik.size < 3000
+        eng.set_buoys(pos0, cell0)
+        cache = {}
+
+        def records(k):                                   # generated chunk-wise, shared with the oracle
+            c = k // chunk
+            if c not in cache:
+                cache.clear()
+                cache[c] = synth.make_records(g, chunk, seed=1000 + c, k0=c * chunk)
+            U, V, IC = cache[c]
+            return U[k % chunk], V[k % chunk], IC[k % chunk]
+        r = eng.track(records, nrec, pos0=pos0, chunk=chunk)
+        p_end, c_end, a_end = eng.get_state()
+    pos, ji, alive = pos0.copy(), cell0.astype(np.int64), np.ones(ik.size, np.int8)
+    same_cell = np.ones(ik.size, bool)
+    ncross = 0
+    for c in range(nrec // chunk):
+        U, V, IC = synth.make_records(g, chunk, seed=1000 + c, k0=c * chunk)
+        ref = corc.track(g, U, V, IC, pos, ji, alive0=alive, history=False)
+        rows = slice(c * chunk + 1, (c + 1) * chunk + 1)
+        alive_rows = ref["mask"][1:] == 1
+        assert np.array_equal(r["mask"][rows], ref["mask"][1:])
+        assert np.array_equal(r["posC"][rows], ref["posC"][1:])                  # bit-exact, fill rows included
+        assert np.abs(r["posG"][rows] - ref["posG"][1:]).max() < LATLON_TOL_DEG
+        assert np.array_equal(r["n_alive"][c * chunk:(c + 1) * chunk], ref["nalive"])
+        ncross += ref["ncross"]
+        # carry the oracle's state: dead buoys keep their last recorded position out of the loop
+        last = np.where(alive_rows.any(axis=0), alive_rows.shape[0] - 1 - np.argmax(alive_rows[::-1], axis=0), -1)
+        for b in np.flatnonzero(last >= 0):
+            pos[b] = ref["posC"][1 + last[b], b]
+        ji, alive = ref["jiT"], ref["alive"]
+    same_cell &= (c_end == ji).all(axis=1)
+    assert np.array_equal(a_end, alive)
+    assert same_cell.mean() == 1.0                                             # north star asks for >= 0.95
+    assert ncross > 10 * ik.size and alive.sum() < ik.size                      # the season is eventful
