@@ -166,6 +166,9 @@ int  st_haversine(int device, int64_t n, double plat, double plon, const double 
  * with a reciprocal + exact-residual sequence; q_fast is that result, q_div the IEEE
  * division, for n host values a.                                                          */
 int  st_selftest_div1000(int device, int64_t n, const double *a, double *q_fast, double *q_div);
+/* Same for the branch-free general division of the inside test (locate.py:72): q_fast = the
+ * kernel's nine-operation sequence, q_div = IEEE division, for n host pairs a/b.            */
+int  st_selftest_divide(int device, int64_t n, const double *a, const double *b, double *q_fast, double *q_div);
 
 #ifdef __cplusplus
 }

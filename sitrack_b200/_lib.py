@@ -31,6 +31,7 @@ SIGNATURES = {
     "st_set_projection": (c_int, [vp, c_dbl, c_dbl]),
     "st_set_kernel_variant": (c_int, [vp, c_int]),
     "st_selftest_div1000": (c_int, [c_int, c_i64, vp, vp, vp]),
+    "st_selftest_divide": (c_int, [c_int, c_i64, vp, vp, vp, vp]),
     "st_set_locate_grid": (c_int, [vp, vp, vp, vp]),
     "st_seed_locate": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp]),
     "st_seed_locate_dev": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp]),

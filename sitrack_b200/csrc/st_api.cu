@@ -119,10 +119,17 @@ static cudaError_t upload(T** dst, const T* src, size_t n)
     return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
 }
 
+static bool g_coord_range_ok = true;
 static cudaError_t upload_pts(pt** dst, const double* Y, const double* X, size_t n)
 {
     std::vector<pt> tmp(n);
-    for (size_t k = 0; k < n; ++k) { tmp[k].y = Y[k]; tmp[k].x = X[k]; }      // layout marshalling only
+    for (size_t k = 0; k < n; ++k) {                                            // layout marshalling only
+        tmp[k].y = Y[k]; tmp[k].x = X[k];
+        // the branch-free divisions of the inside test rely on coordinates of ordinary magnitude
+        const double ay = fabs(Y[k]), ax = fabs(X[k]);
+        if (!(ay <= 16777216.0 && ax <= 16777216.0) || (ay != 0.0 && ay < 7.888609052210118e-31) ||
+            (ax != 0.0 && ax < 7.888609052210118e-31)) g_coord_range_ok = false;
+    }
     return upload(dst, tmp.data(), n);
 }
 
@@ -181,12 +188,17 @@ int st_create(st_ctx** out, int device, int Nj, int Ni, const double* Yf, const 
     st_ctx* c = new st_ctx();
     c->device = device; c->Nj = Nj; c->Ni = Ni;
     const size_t n = (size_t)Nj * Ni;
+    g_coord_range_ok = true;
     cudaError_t e = upload_pts(&c->F, Yf, Xf, n);
     if (e == cudaSuccess && Yu) e = upload_pts(&c->U, Yu, Xu, n);
     if (e == cudaSuccess && Yv) e = upload_pts(&c->V, Yv, Xv, n);
     if (e == cudaSuccess) e = upload(&c->tmask, tmask, n);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { rc = cuda_fail(nullptr, e, "st_create"); st_destroy(c); return rc; }
+    if (!g_coord_range_ok) {
+        st_destroy(c);
+        return fail(nullptr, ST_EINVAL, "st_create: grid coordinates must be km with 2^-100 <= |c| <= 2^24 (or 0) and finite");
+    }
     c->grid.Nj = Nj; c->grid.Ni = Ni; c->grid.uv_strategy = uv_strategy; c->grid.rdt = rdt;
     c->grid.rmin_conc = rmin_conc; c->grid.F = c->F; c->grid.U = c->U; c->grid.V = c->V; c->grid.tmask = c->tmask;
     c->grid.proj = make_proj(70.0, -45.0);
@@ -617,6 +629,19 @@ int st_selftest_div1000(int device, int64_t n, const double* a, double* q_fast, 
     Scratch s; double *d, *f, *r;
     CUS(s.up(&d, a, (size_t)n)); CUS(s.alloc(&f, (size_t)n)); CUS(s.alloc(&r, (size_t)n));
     CUS(launch_div1000(d, f, r, n, 0));
+    CUS(cudaMemcpy(q_fast, f, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CUS(cudaMemcpy(q_div, r, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_selftest_divide(int device, int64_t n, const double* a, const double* b, double* q_fast, double* q_div)
+{
+    if (n < 0 || !a || !b || !q_fast || !q_div) return fail(nullptr, ST_EINVAL, "st_selftest_divide: NULL argument");
+    int rc = use_device(nullptr, device); if (rc) return rc;
+    if (n == 0) return ST_OK;
+    Scratch s; double *da, *db, *f, *r;
+    CUS(s.up(&da, a, (size_t)n)); CUS(s.up(&db, b, (size_t)n)); CUS(s.alloc(&f, (size_t)n)); CUS(s.alloc(&r, (size_t)n));
+    CUS(launch_divcore(da, db, f, r, n, 0));
     CUS(cudaMemcpy(q_fast, f, sizeof(double) * n, cudaMemcpyDeviceToHost));
     CUS(cudaMemcpy(q_div, r, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return ST_OK;

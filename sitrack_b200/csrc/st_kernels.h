@@ -40,6 +40,7 @@ struct StepOut {
 
 cudaError_t launch_advect_step(const AdvectGrid& g, const float* u, const float* v, const float* ic,
                                const BuoyState& s, int jrec, const StepOut& o, int variant, cudaStream_t st);
+cudaError_t launch_divcore(const double* a, const double* b, double* q_fast, double* q_div, long long n, cudaStream_t st);
 cudaError_t launch_div1000(const double* a, double* q_fast, double* q_div, long long n, cudaStream_t st);
 cudaError_t launch_advect_multi(const AdvectGrid& g, const float* rec0, long long rec_stride, int nrec,
                                 const BuoyState& s, int jrec0, const StepOut& o, long long out_stride,

@@ -217,7 +217,7 @@ k_advect_pipe(const AdvectGrid g, const float* __restrict__ u, const float* __re
         asm volatile("cp.async.commit_group;" ::: "memory");
         // ---- inside test, rows, state ----------------------------------------------------------
         if (act) {
-            cross = !inside_quad2(outp.y, outp.x, bl, br, ur, ul);
+            cross = !inside_quad_div(outp.y, outp.x, bl, br, ur, ul);
             st_stream_pt(s.pos + p, outp);
         }
         if (valid) {

@@ -383,3 +383,33 @@ def test_full_season_config2_vs_oracle(torch, corc):
     assert np.array_equal(a_end, alive)
     assert same_cell.mean() == 1.0                                             # north star asks for >= 0.95
     assert ncross > 10 * ik.size and alive.sum() < ik.size                      # the season is eventful
+
+
+def test_div_core_is_ieee_division(sit):
+    """The branch-free division of the inside test (xints, locate.py:72) equals IEEE division: random
+    operands over the magnitudes km coordinates produce, zeros, signs, and quotients built to sit next
+    to rounding midpoints."""
+    from sitrack_b200 import _lib
+    rng = np.random.default_rng(33)
+    n = 3_000_000
+    a = rng.standard_normal(n) * 10.0 ** rng.uniform(-14, 9, n)
+    b = rng.standard_normal(n) * 10.0 ** rng.uniform(-13, 5, n)
+    a[:1000] = 0.0; a[1000:2000] = -0.0
+    # adversarial: choose b and a quotient q, then a = RN(b * (q + ulp/2)) and its neighbours
+    q = rng.uniform(1, 2, 1_000_000) * rng.choice([-1.0, 1.0], 1_000_000)
+    bb = rng.uniform(1, 2, 1_000_000) * 10.0 ** rng.integers(-6, 5, 1_000_000)
+    mid = ((np.abs(q) + np.spacing(np.abs(q)) / 2) * np.sign(q)).astype(np.longdouble) * bb.astype(np.longdouble)
+    mids = mid.astype(np.float64)
+    aa = np.concatenate([mids, np.nextafter(mids, np.inf), np.nextafter(mids, -np.inf)])
+    a = np.ascontiguousarray(np.concatenate([a, aa]))
+    b = np.ascontiguousarray(np.concatenate([b, bb, bb, bb]))
+    keep = b != 0
+    a, b = np.ascontiguousarray(a[keep]), np.ascontiguousarray(b[keep])
+    qf = np.empty_like(a); qd = np.empty_like(a)
+    _lib.check(_lib.lib().st_selftest_divide(0, a.size, a.ctypes.data, b.ctypes.data, qf.ctypes.data, qd.ctypes.data))
+    assert np.array_equal(qd, a / b)
+    assert np.array_equal(qf, qd)
+    # the only bit-level difference allowed: the sign of a zero quotient when a = -0 (the kernel's
+    # numerator is (y-y1)*(x2-x1) with y-y1 > 0, never -0; and x <= xints cannot see the sign of zero)
+    nz = qd != 0
+    assert np.array_equal(np.signbit(qf[nz]), np.signbit(qd[nz])) and (qf[~nz] == 0).all()
