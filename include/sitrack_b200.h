@@ -55,8 +55,10 @@ int  st_create(st_ctx **out, int device, int Nj, int Ni,
                int uv_strategy, double rdt, double rmin_conc);
 void st_destroy(st_ctx *ctx);
 
-/* 0 (default) = tuned k_advect_step, 1 = k_advect_step_v1, the straightforward kernel kept as
- * A/B reference (also selected by the environment variable SITRACK_B200_KERNEL=v1).     */
+/* Step-kernel variant, all bit-identical in their results: 0 (default) tuned k_advect_step
+ * (128 threads x 10 blocks/SM); 1 k_advect_step_v1, the straightforward kernel kept as A/B
+ * reference (also SITRACK_B200_KERNEL=v1); 4 / 9 the tuned kernel at 128x8 / 256x4;
+ * 8 k_advect_pipe, the persistent TMA + cp.async pipelined form.                          */
 int  st_set_kernel_variant(st_ctx *ctx, int variant);
 
 /* Polar-stereographic parameters of CartNPSkm2Geo1D (util.py:413: lat0=70, lon0=-45). */

@@ -213,7 +213,7 @@ int st_create(st_ctx** out, int device, int Nj, int Ni, const double* Yf, const 
 
 int st_set_kernel_variant(st_ctx* c, int variant)
 {
-    if (!c || variant < 0 || variant > 9) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 (tuned), 1 (v1), 2..7 (launch-bound experiments), 8 (pipelined)");
+    if (!c || variant < 0 || variant > 9 || variant == 2 || variant == 3 || (variant >= 5 && variant <= 7)) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 tuned, 1 v1, 4/9 other launch shapes, 8 pipelined");
     c->variant = variant;
     return ST_OK;
 }

@@ -129,10 +129,10 @@ def test_track_golden(torch, corc, gold_track, name, multi):
     assert np.abs(ll - want).max() < LATLON_TOL_DEG                  # also for the -9999 rows (:493)
 
 
-@pytest.mark.parametrize("variant", [1, 5, 8])
+@pytest.mark.parametrize("variant", [1, 4, 8, 9])
 @pytest.mark.parametrize("name", list(TRACK_CASES))
 def test_track_golden_other_kernels(torch, gold_track, name, variant):
-    """v1 (straightforward), a 128-thread launch-bound variant and the persistent TMA/cp.async
+    """v1 (straightforward), the other launch shapes of the tuned kernel and the persistent TMA/cp.async
     pipelined kernel reproduce the reference's golden trajectories bit for bit too."""
     T, g = gold_track
     c = TRACK_CASES[name]
