@@ -263,8 +263,33 @@ def run_ours(args):
             "peak_source": peak_src, "alg_bytes_per_buoy_step": B_ALG,
             "buoy_steps_per_launch": bsteps / K, "us_per_launch": round(ms / K * 1e3, 2)}
 
-    # -- optional: the same loop with the per-record NCCL all-gather of positions ----------------
     extra = {}
+    # -- small clouds: the season path, R resident records per launch of k_advect_multi -----------
+    if wl["grid"] == "nanuk4" or args.multi:
+        Rm = args.multi or R
+        rec_t = torch.from_numpy(np.stack([U, V, IC], axis=1).astype(np.float32)).to(dev).contiguous()[:Rm]
+        m_yx = torch.empty((Rm, nP, 2), dtype=torch.float64, device=dev)
+        m_ll = torch.empty((Rm, nP, 2), dtype=torch.float64, device=dev)
+        m_mk = torch.empty((Rm, nP), dtype=torch.int8, device=dev)
+        nl = max(3, min(50, K // Rm))
+        m_na = torch.zeros((nl + 3, Rm), dtype=torch.int64, device=dev)
+        reset()
+        for i in range(3):
+            eng.step_multi(rec_t, i * Rm, m_yx, m_ll, m_mk, m_na[i], stream)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        for i in range(3, 3 + nl):
+            eng.step_multi(rec_t, i * Rm, m_yx, m_ll, m_mk, m_na[i], stream)
+        t1.record(stream)
+        barrier()
+        ms_m, bs_m = reduce_max_sum(t0.elapsed_time(t1), int(m_na[3:].sum().item()))
+        extra["season_path"] = {"value": bs_m / (ms_m * 1e-3), "unit": "buoy-steps/s", "records_per_launch": Rm,
+                                "launches": nl, "us_per_record": round(ms_m * 1e3 / (nl * Rm), 3),
+                                "what": "k_advect_multi: each thread runs its buoy through %d resident records "
+                                        "per launch, trajectory rows written every record" % Rm}
+        del rec_t, m_yx, m_ll, m_mk
+    # -- optional: the same loop with the per-record NCCL all-gather of positions ----------------
     if world > 1 and not args.no_allgather:
         comm = torch.cuda.Stream(dev)
         gathered = torch.empty((world * nP_max(nP, dist, dev), 2), dtype=torch.float64, device=dev)
@@ -531,6 +556,7 @@ def main():
     ap.add_argument("--workload", default="cfg5", choices=list(WORKLOADS))
     ap.add_argument("--kernel", default="tuned", help="k_advect_step variant: tuned, v1, or an integer launch-bound experiment")
     ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--multi", type=int, default=0, help="also time k_advect_multi with this many records per launch")
     ap.add_argument("--no-allgather", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2000, help="buoys in the Python cpu_baseline sample")

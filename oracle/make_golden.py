@@ -209,7 +209,18 @@ def main():
         small["ResKM"], small["tmask"], xIceConc=xic)
     near = np.array([quiet(sit.NearestPoint, (SG[k, 0], SG[k, 1]), small["latT"], small["lonT"],
                            rd_found_km=2.5, resolkm=small["ResKM"], max_itr=10) for k in range(SG.shape[0])])
+    # FCC (locate.py:139-218), the geographic variant: T-centred cells whose vertices are F-points
+    latF, lonF = synth.grid.km_to_latlon(small["Yf"], small["Xf"])
+    lonF = np.mod(lonF, 360.)
+    kk = [k for k in range(SG.shape[0]) if near[k][0] >= 3 and near[k][1] >= 3
+          and near[k][0] < small["Nj"] - 3 and near[k][1] < small["Ni"] - 3][:60]
+    fcc_ji, fcc_vrt = [], []
+    for k in kk:
+        ji, vr = quiet(sit.FCC, (SG[k, 0], SG[k, 1]), small["latT"], small["lonT"], latF, lonF, cellType='T',
+                       rd_found_km=2.5, resolkm=small["ResKM"], max_itr=10)
+        fcc_ji.append(ji); fcc_vrt.append(np.array(vr))
     np.savez_compressed(os.path.join(GOLD, "seedinit_small.npz"), **grid_arrays(small), ic0=ICs[0],
+                        fcc_idx=np.array(kk), fcc_ji=np.array(fcc_ji), fcc_vrt=np.array(fcc_vrt), g_latF=latF, g_lonF=lonF,
                         ids=ids, SG=SG, SC=SC, out_nP=nP, out_SG=pSG, out_SC=pSC, out_IDs=pIDs,
                         out_jiT=zjiT, out_VRTCS=zJIvrt, out_iKeep=iKeep, out_nearest=near)
     print("seedinit_small: %d seeds -> %d kept" % (SG.shape[0], nP))

@@ -56,6 +56,46 @@ def TheCell(pyx, kjiT, pYf, pXf, iverbose=0):
     return lPin, ji, np.array(v, dtype=int).T.copy()
 
 
+def NorthStereoProj(pphi, plam, lam0=0., phi0=90.):
+    """locate.py:23-43 -- spherical (R=6300 km) stereographic projection about (phi0, lam0) -> (y, x) km.
+    Not on the tracker's path (only FCC uses it, on a 5x5 neighbourhood): plain numpy host helper."""
+    to_rad = 3.141592653589793 / 180.
+    s0, c0 = np.sin(to_rad * phi0), np.cos(to_rad * phi0)
+    sp, cp = np.sin(to_rad * pphi), np.cos(to_rad * pphi)
+    cl = np.cos(to_rad * (plam - lam0))
+    zk = 2. * 6300. / (1. + s0 * sp + c0 * cp * cl)
+    return zk * (c0 * sp - s0 * cp * cl), zk * cp * np.sin(to_rad * (plam - lam0))
+
+
+def FCC(pntGcoor, pLat, pLon, pLatC, pLonC, cellType='T', rd_found_km=10., resolkm=[],
+        ji_prv=(), np_box_r=10, max_itr=5, pntID=None, iverbose=0):
+    """locate.py:139-218 -- geographic-coordinate variant of the containing-cell search (unused by the
+    tracker): nearest `cellType` point on the device, then TheCell on a locally projected 5x5 box.
+    -> [jX,iX], vertices (4,2).  Upstream quirks kept: the vertex offsets use the UPDATED jX,iX, and an
+    unfound point raises (upstream returns an unbound KVRTCS)."""
+    nhb = 2
+    if cellType not in ('T', 'F'):
+        print('ERROR [FCC]: for now we just expect the mesh to be centered on "T" or "F" points.')
+        raise SystemExit(0)
+    (zlat, zlon) = pntGcoor
+    (jX, iX) = NearestPoint(pntGcoor, pLat, pLon, rd_found_km=rd_found_km, resolkm=resolkm,
+                            ji_prv=ji_prv, np_box_r=np_box_r, max_itr=max_itr)
+    if jX < 0 or iX < 0:
+        raise UnboundLocalError("FCC: no nearest point found (upstream fails on an unbound `KVRTCS` here)")
+    zYC, zXC = NorthStereoProj(pLatC[jX - nhb:jX + 3, iX - nhb:iX + 3], pLonC[jX - nhb:jX + 3, iX - nhb:iX + 3],
+                               lam0=pLon[jX, iX], phi0=pLat[jX, iX])
+    zy0, zx0 = NorthStereoProj(np.array([zlat]), np.array([zlon]), lam0=pLon[jX, iX], phi0=pLat[jX, iX])
+    lPin, [jM, iM], KVRTCS = TheCell((float(zy0[0]), float(zx0[0])), (nhb, nhb), zYC, zXC)
+    jX = jM + jX - nhb
+    iX = iM + iX - nhb
+    KVRTCS[:, 0] = KVRTCS[:, 0] + jX - nhb
+    KVRTCS[:, 1] = KVRTCS[:, 1] + iX - nhb
+    if not lPin:
+        print('WARNING [SeedInit()]: could not find the proper F-point cell!!!')
+        print('         => when lookin for point:', zlat, zlon)
+    return [jX, iX], KVRTCS
+
+
 def NearestPointBatch(latlon, pLat, pLon, rd_found_km=10., resolkm=None, max_itr=5, brute=False):
     """(n,2) [lat,lon] -> (ji (n,2) with -1,-1 when not found, dist_km (n,))."""
     from .engine import TrackEngine

@@ -413,3 +413,100 @@ def test_div_core_is_ieee_division(sit):
     # numerator is (y-y1)*(x2-x1) with y-y1 > 0, never -0; and x <= xints cannot see the sign of zero)
     nz = qd != 0
     assert np.array_equal(np.signbit(qf[nz]), np.signbit(qd[nz])) and (qf[~nz] == 0).all()
+
+
+# ---- full BASELINE size: size-independent properties ----------------------------------------------------
+
+def test_properties_at_full_size(torch, sit, corc):
+    """12.5 M buoys on the 1/12-degree-class grid (config 5's per-GPU share), where the oracle is too
+    slow to run everything: (1) a zero-velocity record is the identity on positions and cells and
+    leaves everyone alive, (2) two runs are bit-identical (no atomics or ordering in the results),
+    (3) tracking the two halves of the cloud separately equals tracking it whole (buoys never
+    interact: the sharding property the multi-GPU path rests on), (4) alive counts never grow and
+    match the row masks, (5) lat/lon rows invert back to the km rows within 1e-6 km, (6) a random
+    20 k-buoy sub-sample matches the C oracle bit for bit over all records."""
+    import synth
+    g = synth.make_grid(**synth.GRID_PRESETS["arctic12"], seed=0)
+    nrec = 6
+    U, V, IC = synth.make_records(g, nrec, seed=1)
+    ids, _, SC = synth.dense_seeds(g, 12_500_000, IC[0], seed=3, with_latlon=False)
+    dev = torch.device("cuda", 0)
+    SC_t = torch.from_numpy(SC).to(dev)
+    SG_t = torch.empty_like(SC_t)
+    with engine_for(g) as eng:
+        eng.set_locate_grid(g["latT"], g["lonT"], g["ResKM"])
+        sit._lib.check(eng.L.st_xy2latlon_dev(SC_t.shape[0], SC_t.data_ptr(), SG_t.data_ptr(), 70.0, -45.0, None))
+        SG_t[:, 1] = torch.remainder(SG_t[:, 1], 360.0)
+        cell_t, near_t, keep_t = eng.seed_locate_dev(SG_t, SC_t, torch.from_numpy(IC[0]).to(dev))
+        kp = keep_t.bool()
+        pos0, cell0 = SC_t[kp].contiguous(), cell_t[kp].contiguous()
+        nP = pos0.shape[0]
+        assert nP > 12_000_000
+        eng.record_slots(nrec + 1)
+        for k in range(nrec):
+            st = eng.staging(k); st[0], st[1], st[2] = U[k], V[k], IC[k]; eng.submit_record(k)
+        st = eng.staging(nrec); st[0], st[1] = 0.0, 0.0; st[2] = IC[0]; eng.submit_record(nrec)
+        torch.cuda.synchronize()
+
+        def run(p0, c0, recs):
+            n = p0.shape[0]
+            eng.set_buoys_dev(p0, c0)
+            yx = torch.empty((len(recs), n, 2), dtype=torch.float64, device=dev)
+            ll = torch.empty((len(recs), n, 2), dtype=torch.float64, device=dev)
+            mk = torch.empty((len(recs), n), dtype=torch.int8, device=dev)
+            na = torch.zeros((len(recs),), dtype=torch.int64, device=dev)
+            for i, r in enumerate(recs):
+                eng.step(r, i, yx[i], ll[i], mk[i], na[i:i + 1])
+            torch.cuda.synchronize()
+            _, c, a = eng.get_state()
+            return yx, ll, mk, na.cpu().numpy(), c, a
+
+        # (1) identity under zero velocity
+        yx, ll, mk, na, c, a = run(pos0, cell0, [nrec])
+        assert torch.equal(yx[0], pos0) and bool((mk[0] == 1).all()) and na[0] == nP
+        assert np.array_equal(c, cell0.cpu().numpy()) and a.all()
+        del yx, ll, mk
+        # (2) determinism, (4) alive counts
+        recs = list(range(nrec))
+        yx1, ll1, mk1, na1, c1, a1 = run(pos0, cell0, recs)
+        yx2, ll2, mk2, na2, c2, a2 = run(pos0, cell0, recs)
+        assert torch.equal(yx1, yx2) and torch.equal(ll1, ll2) and torch.equal(mk1, mk2)
+        assert np.array_equal(c1, c2) and np.array_equal(a1, a2) and np.array_equal(na1, na2)
+        del yx2, ll2, mk2
+        assert (np.diff(na1) <= 0).all() and na1[0] == nP and na1[-1] < nP
+        assert np.array_equal(mk1.sum(dim=1).cpu().numpy(), na1)          # row masks = buoys alive at record start
+        assert int(a1.sum()) <= na1[-1]
+        # (5) projection round trip on the last row (alive buoys)
+        sel = mk1[-1] == 1
+        llsel = ll1[-1][sel].contiguous()
+        yx_back = sit.Geo2CartNPSkm1D(llsel[:200_000].cpu().numpy())
+        assert np.abs(yx_back - yx1[-1][sel][:200_000].cpu().numpy()).max() < 1e-6
+        # (3) shard invariance: halves tracked separately == whole
+        h = (nP // 2 // 256) * 256
+        yxa, _, mka, naa, ca, aa = run(pos0[:h].contiguous(), cell0[:h].contiguous(), recs)
+        assert torch.equal(yxa, yx1[:, :h]) and torch.equal(mka, mk1[:, :h]) and np.array_equal(ca, c1[:h])
+        yxb, _, mkb, nab, cb, ab = run(pos0[h:].contiguous(), cell0[h:].contiguous(), recs)
+        assert torch.equal(yxb, yx1[:, h:]) and np.array_equal(cb, c1[h:]) and np.array_equal(naa + nab, na1)
+        del yxa, yxb, mka, mkb
+        # (6) sub-sample against the oracle
+        rng = np.random.default_rng(5)
+        sub = np.sort(rng.choice(nP, 20_000, replace=False))
+        p_sub, c_sub = pos0.cpu().numpy()[sub], cell0.cpu().numpy()[sub]
+        ref = corc.track(g, U, V, IC, p_sub, c_sub.astype(np.int64), history=False)
+        sub_t = torch.from_numpy(sub).to(dev)
+        assert np.array_equal(yx1[:, sub_t].cpu().numpy(), ref["posC"][1:])
+        assert np.array_equal(mk1[:, sub_t].cpu().numpy(), ref["mask"][1:])
+        assert np.array_equal(c1[sub], ref["jiT"]) and np.array_equal(a1[sub], ref["alive"])
+        assert np.abs(ll1[:, sub_t].cpu().numpy() - ref["posG"][1:]).max() < LATLON_TOL_DEG
+
+
+def test_fcc_golden(sit, gold_seed):
+    """FCC (locate.py:139-218, geographic variant, not on the tracker's path) against the reference's
+    answers: nearest T on the device, local spherical projection, TheCell on the 5x5 box."""
+    S, g = gold_seed
+    import contextlib, io
+    for n, k in enumerate(S["fcc_idx"][:25]):
+        with contextlib.redirect_stdout(io.StringIO()):
+            ji, vr = sit.FCC((S["SG"][k, 0], S["SG"][k, 1]), g["latT"], g["lonT"], g["latF"], g["lonF"], cellType='T',
+                             rd_found_km=2.5, resolkm=g["ResKM"], max_itr=10)
+        assert list(ji) == list(S["fcc_ji"][n]) and np.array_equal(np.asarray(vr), S["fcc_vrt"][n])
