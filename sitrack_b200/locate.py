@@ -6,6 +6,8 @@ for real work).  No CPU fallback.
 import numpy as np
 
 from . import _lib, config
+
+__all__ = ['find_ji_of_min', 'NorthStereoProj', 'IsInsideQuadrangle', 'IsInsideQuadrangleBatch', 'TheCell', 'FCC', 'NearestPoint', 'NearestPointBatch', 'FindContainingCell']
 from ._lib import as_c, check, hptr
 
 

@@ -9,8 +9,10 @@ singleton dimensions, so the whole CLI runs on synthetic data without netCDF:
 The km coordinates of the grid come from the device projection kernel
 (ConvertGeo2CartesianNPSkm -> st_latlon2xy) instead of cartopy.
 """
-from os import path
-from sys import argv
+import math
+import os
+import re
+import sys
 
 import numpy as np
 
@@ -24,47 +26,49 @@ __all__ = ["tunits_default", "FillValue", "GetModelGrid", "GetModelUVGrid", "Get
 tunits_default = 'seconds since 1970-01-01 00:00:00'     # ncio.py:15
 FillValue = -9999.                                       # ncio.py:19
 
+_TIME_VARS = ("time", "time_counter", "time_pos")
+_DIM_OF = {"time_counter": "time_counter", "time": "time", "id_buoy": "buoy"}
 
-class _NpzVar:
-    def __init__(self, a, units=None):
-        self.a, self.units = a, units
 
-    def __getitem__(self, k):
-        return self.a[k]
+def _die(msg):
+    print(msg)
+    raise SystemExit(0)
 
-    @property
-    def shape(self):
-        return self.a.shape
+
+class _Var:
+    """Array with a `.units` attribute, indexable like a netCDF4 variable."""
+
+    def __init__(self, data, units=None):
+        self._d, self.units = data, units
+
+    def __getitem__(self, key):
+        return self._d[key]
+
+    shape = property(lambda self: self._d.shape)
+
+
+class _Dim:
+    def __init__(self, size):
+        self.size = size
 
 
 class _NpzDataset:
-    """Read-only view of an .npz laid out like the netCDF files the tracker reads."""
-    _time_vars = ("time", "time_counter", "time_pos")
+    """Read-only stand-in for netCDF4.Dataset over an .npz with the same variable names."""
 
     def __init__(self, fn):
-        self.z = np.load(fn, allow_pickle=False)
-        self.variables = {k: _NpzVar(self.z[k], tunits_default if k in self._time_vars else None)
-                          for k in self.z.files}
+        self._z = np.load(fn, allow_pickle=False)
+        names = self._z.files
+        self.variables = {n: _Var(self._z[n], tunits_default if n in _TIME_VARS else None) for n in names}
+        self.dimensions = {d: _Dim(self._z[v].shape[0]) for v, d in _DIM_OF.items() if v in names}
 
-        class _Dim:
-            def __init__(self, n):
-                self.size = n
-        self.dimensions = {}
-        if "time_counter" in self.z.files:
-            self.dimensions["time_counter"] = _Dim(self.z["time_counter"].shape[0])
-        if "time" in self.z.files:
-            self.dimensions["time"] = _Dim(self.z["time"].shape[0])
-        if "id_buoy" in self.z.files:
-            self.dimensions["buoy"] = _Dim(self.z["id_buoy"].shape[0])
+    def close(self):
+        self._z.close()
 
     def __enter__(self):
         return self
 
-    def __exit__(self, *a):
+    def __exit__(self, *exc):
         self.close()
-
-    def close(self):
-        self.z.close()
 
 
 def open_dataset(fn):
@@ -72,256 +76,215 @@ def open_dataset(fn):
     if str(fn).endswith(".npz"):
         return _NpzDataset(fn)
     try:
-        from netCDF4 import Dataset
+        import netCDF4
     except ImportError as e:
         raise ImportError("netCDF4 is needed to read '%s' (or pass the .npz equivalent)" % fn) from e
-    return Dataset(fn)
+    return netCDF4.Dataset(fn)
 
 
-def _lvl(v, n):
-    """v[0,..,0,:,:] with n leading singleton indices when they exist (npz files may omit them)."""
-    a = np.asarray(v[:])
-    while a.ndim > 2:
-        a = a[0]
-    return a
+def _plane(var):
+    """The horizontal (Nj,Ni) plane of a mesh_mask variable: leading singleton axes dropped."""
+    a = np.asarray(var[:])
+    return a.reshape(a.shape[-2:])
+
+
+def _read_planes(fn, names):
+    chck4f(fn)
+    with open_dataset(fn) as ds:
+        return [_plane(ds.variables[n]) for n in names]
+
+
+def _to_km(lat, lon):
+    return ConvertGeo2CartesianNPSkm(lat, np.mod(lon, 360.))
 
 
 def GetModelGrid(fNCmeshmask, alsoF=False):
     """ncio.py:22-63 -> kmaskt, latT, lonT(0..360), Yt, Xt, Yf, Xf [km], ResKM [, kmaskf, latF, lonF]"""
-    chck4f(fNCmeshmask)
-    with open_dataset(fNCmeshmask) as id_mm:
-        kmaskt = _lvl(id_mm.variables['tmask'], 2)
-        zlonF, zlatF = _lvl(id_mm.variables['glamf'], 1), _lvl(id_mm.variables['gphif'], 1)
-        zlonT, zlatT = _lvl(id_mm.variables['glamt'], 1), _lvl(id_mm.variables['gphit'], 1)
-        ze1T = _lvl(id_mm.variables['e1t'], 1) / 1000.
-        ze2T = _lvl(id_mm.variables['e2t'], 1) / 1000.
-        if alsoF:
-            kmaskf = _lvl(id_mm.variables['fmask'], 2)
-    kmaskt = np.array(kmaskt, dtype='i1')
-    zlonT = np.mod(zlonT, 360.)
-    zlonF = np.mod(zlonF, 360.)
-    zYt, zXt = ConvertGeo2CartesianNPSkm(zlatT, zlonT)
-    zYf, zXf = ConvertGeo2CartesianNPSkm(zlatF, zlonF)
-    zResKM = np.sqrt(ze1T * ze1T + ze2T * ze2T).astype(np.float64)
-    if alsoF:
-        return kmaskt, zlatT, zlonT, zYt, zXt, zYf, zXf, zResKM, kmaskf, zlatF, zlonF
-    return kmaskt, zlatT, zlonT, zYt, zXt, zYf, zXf, zResKM
+    want = ['tmask', 'glamt', 'gphit', 'glamf', 'gphif', 'e1t', 'e2t'] + (['fmask'] if alsoF else [])
+    got = dict(zip(want, _read_planes(fNCmeshmask, want)))
+    kmaskt = np.array(got['tmask'], dtype='i1')
+    lonT, lonF = np.mod(got['glamt'], 360.), np.mod(got['glamf'], 360.)
+    Yt, Xt = _to_km(got['gphit'], lonT)
+    Yf, Xf = _to_km(got['gphif'], lonF)
+    e1, e2 = got['e1t'] / 1000., got['e2t'] / 1000.
+    res = np.asarray(np.sqrt(e1 * e1 + e2 * e2), dtype=np.float64)
+    base = (kmaskt, got['gphit'], lonT, Yt, Xt, Yf, Xf, res)
+    return base + (got['fmask'], got['gphif'], lonF) if alsoF else base
 
 
 def GetModelUVGrid(fNCmeshmask):
     """ncio.py:66-92 -> Yv, Xv, Yu, Xu [km]"""
-    chck4f(fNCmeshmask)
-    with open_dataset(fNCmeshmask) as id_mm:
-        zlonV, zlatV = _lvl(id_mm.variables['glamv'], 1), _lvl(id_mm.variables['gphiv'], 1)
-        zlonU, zlatU = _lvl(id_mm.variables['glamu'], 1), _lvl(id_mm.variables['gphiu'], 1)
-    zYv, zXv = ConvertGeo2CartesianNPSkm(zlatV, np.mod(zlonV, 360.))
-    zYu, zXu = ConvertGeo2CartesianNPSkm(zlatU, np.mod(zlonU, 360.))
-    return zYv, zXv, zYu, zXu
+    lonV, latV, lonU, latU = _read_planes(fNCmeshmask, ['glamv', 'gphiv', 'glamu', 'gphiu'])
+    return _to_km(latV, lonV) + _to_km(latU, lonU)
 
 
 def GetSeedMask(fFSmask, mvar='tmask'):
     chck4f(fFSmask)
-    with open_dataset(fFSmask) as id_mm:
-        kmaskt = np.asarray(id_mm.variables[mvar][:, :])
-    return np.array(kmaskt, dtype='i1')
+    with open_dataset(fFSmask) as ds:
+        return np.array(ds.variables[mvar][:, :], dtype='i1')
 
 
 def GetModelSeaIceConc(fNCsi3, name='siconc', krec=0, expected_shape=[]):
     chck4f(fNCsi3)
-    print('    * [GetModelSeaIceConc]: reading "' + name + '" at record ' + str(krec) + ' in ' + fNCsi3 + ' !')
-    with open_dataset(fNCsi3) as id_si3:
-        zsic = np.asarray(id_si3.variables[name][krec, :, :])
-    if len(expected_shape) > 0 and np.shape(zsic) != tuple(expected_shape):
-        print('ERROR [GetModelSeaIceConc]: wrong shape for sea-ice concentration read:', np.shape(zsic),
-              ', expected:', expected_shape)
-        raise SystemExit(0)
-    return zsic
+    print('    * [GetModelSeaIceConc]: reading "%s" at record %d in %s !' % (name, krec, fNCsi3))
+    with open_dataset(fNCsi3) as ds:
+        sic = np.asarray(ds.variables[name][krec, :, :])
+    if len(expected_shape) > 0 and sic.shape != tuple(expected_shape):
+        _die('ERROR [GetModelSeaIceConc]: wrong shape for sea-ice concentration read: %s, expected: %s'
+             % (sic.shape, expected_shape))
+    return sic
+
+
+# (variable, dtype, dims, units, use fill value) of the buoy-cloud file, ncio.py:153-172
+_CLOUD_VARS = [
+    ('latitude', 'f4', 'degrees north'), ('longitude', 'f4', 'degrees south'),      # sic (ncio.py:164)
+    ('y_pos', 'f4', 'km'), ('x_pos', 'f4', 'km'),
+]
 
 
 def ncSaveCloudBuoys(cf_out, ptime, pIDs, pY, pX, pLat, pLon, mask=[], xtime=[],
                      tunits=tunits_default, fillVal=FillValue, corigin=None):
     """ncio.py:131-197: time i4, buoy i4, id_buoy i8, latitude/longitude/y_pos/x_pos f4 (time,buoy)
-    [+ mask i1, time_pos i4].  Writes netCDF4 when available and the name does not end in .npz,
-    otherwise an .npz with the same variables and dtypes."""
+    [+ mask i1, time_pos i4].  netCDF4 when available and the name does not end in .npz, otherwise an
+    .npz with the same variables and dtypes."""
     print('\n *** [ncSaveCloudBuoys]: About to generate file: ' + cf_out + ' ...')
-    (Nt,) = np.shape(ptime)
-    (Nb,) = np.shape(pIDs)
-    if np.shape(pY) != (Nt, Nb) or np.shape(pX) != (Nt, Nb) or np.shape(pLat) != (Nt, Nb) or np.shape(pLon) != (Nt, Nb):
-        print('ERROR [ncSaveCloudBuoys]: one of the 2D arrays has a wrong shape!!!')
-        raise SystemExit(0)
-    lSaveMask = (np.shape(mask) == (Nt, Nb))
-    lSaveTime = (np.shape(xtime) == (Nt, Nb))
-    use_npz = str(cf_out).endswith(".npz")
-    if not use_npz:
+    shp = (np.shape(ptime)[0], np.shape(pIDs)[0])
+    fields = dict(latitude=pLat, longitude=pLon, y_pos=pY, x_pos=pX)
+    if any(np.shape(a) != shp for a in fields.values()):
+        _die('ERROR [ncSaveCloudBuoys]: one of the 2D arrays has a wrong shape!!!')
+    extra = {}
+    if np.shape(mask) == shp:
+        extra['mask'] = ('i1', np.asarray(mask))
+    if np.shape(xtime) == shp:
+        extra['time_pos'] = ('i4', np.asarray(xtime))
+    nc = None
+    if not str(cf_out).endswith(".npz"):
         try:
-            from netCDF4 import Dataset
+            import netCDF4 as nc
         except ImportError:
-            use_npz = True
-            cf_out = cf_out + ".npz"
+            cf_out += ".npz"
             print('      (netCDF4 not available: writing ' + cf_out + ' with the same variables)')
-    if use_npz:
-        out = dict(time=np.asarray(ptime).astype('i4'), buoy=np.arange(Nb, dtype='i4'),
-                   id_buoy=np.asarray(pIDs).astype('i8'), latitude=np.asarray(pLat, 'f4'),
-                   longitude=np.asarray(pLon, 'f4'), y_pos=np.asarray(pY, 'f4'), x_pos=np.asarray(pX, 'f4'))
-        if lSaveMask:
-            out["mask"] = np.asarray(mask, 'i1')
-        if lSaveTime:
-            out["time_pos"] = np.asarray(xtime).astype('i4')
+    if nc is None:
+        out = dict(time=np.asarray(ptime).astype('i4'), buoy=np.arange(shp[1], dtype='i4'),
+                   id_buoy=np.asarray(pIDs).astype('i8'))
+        out.update({k: np.asarray(v, 'f4') for k, v in fields.items()})
+        out.update({k: v.astype(dt) for k, (dt, v) in extra.items()})
         np.savez_compressed(cf_out, **out)
-        print('      ===> ' + cf_out + ' saved!')
-        return 0
-    f_out = Dataset(cf_out, 'w', format='NETCDF4')
-    f_out.createDimension('time', None)
-    f_out.createDimension('buoy', Nb)
-    v_time = f_out.createVariable('time', 'i4', ('time',))
-    v_buoy = f_out.createVariable('buoy', 'i4', ('buoy',))
-    v_bid = f_out.createVariable('id_buoy', 'i8', ('buoy',))
-    kw = dict(fill_value=fillVal, zlib=True, complevel=9)
-    x_lat = f_out.createVariable('latitude', 'f4', ('time', 'buoy',), **kw)
-    x_lon = f_out.createVariable('longitude', 'f4', ('time', 'buoy',), **kw)
-    x_ykm = f_out.createVariable('y_pos', 'f4', ('time', 'buoy',), **kw)
-    x_xkm = f_out.createVariable('x_pos', 'f4', ('time', 'buoy',), **kw)
-    v_time.units = tunits
-    v_bid.units = 'ID of buoy'
-    x_lat.units = 'degrees north'
-    x_lon.units = 'degrees south'          # sic (ncio.py:164)
-    x_ykm.units = 'km'
-    x_xkm.units = 'km'
-    if lSaveMask:
-        v_mask = f_out.createVariable('mask', 'i1', ('time', 'buoy',), zlib=True, complevel=9)
-    if lSaveTime:
-        x_tim = f_out.createVariable('time_pos', 'i4', ('time', 'buoy',), **kw)
-        x_tim.units = tunits
-    v_buoy[:] = np.arange(Nb, dtype='i8')
-    v_bid[:] = pIDs[:]
-    for jt in range(Nt):
-        v_time[jt] = ptime[jt]
-        x_lat[jt, :] = pLat[jt, :]
-        x_lon[jt, :] = pLon[jt, :]
-        x_ykm[jt, :] = pY[jt, :]
-        x_xkm[jt, :] = pX[jt, :]
-        if lSaveMask:
-            v_mask[jt, :] = mask[jt, :]
-        if lSaveTime:
-            x_tim[jt, :] = xtime[jt, :]
-    if corigin:
-        f_out.Origin = corigin
-    f_out.About = 'Lagrangian sea-ice drift'
-    f_out.Author = 'Generated with `' + path.basename(argv[0]) + '` of `sitrack` (L. Brodeau, 2023)'
-    f_out.close()
+    else:
+        with nc.Dataset(cf_out, 'w', format='NETCDF4') as f:
+            f.createDimension('time', None)
+            f.createDimension('buoy', shp[1])
+            vt = f.createVariable('time', 'i4', ('time',)); vt.units = tunits
+            f.createVariable('buoy', 'i4', ('buoy',))[:] = np.arange(shp[1], dtype='i8')
+            vid = f.createVariable('id_buoy', 'i8', ('buoy',)); vid.units = 'ID of buoy'
+            vid[:] = pIDs[:]
+            zkw = dict(zlib=True, complevel=9)
+            handles = {}
+            for name, dt, units in _CLOUD_VARS:
+                handles[name] = f.createVariable(name, dt, ('time', 'buoy'), fill_value=fillVal, **zkw)
+                handles[name].units = units
+            if 'mask' in extra:
+                handles['mask'] = f.createVariable('mask', 'i1', ('time', 'buoy'), **zkw)
+            if 'time_pos' in extra:
+                handles['time_pos'] = f.createVariable('time_pos', 'i4', ('time', 'buoy'), fill_value=fillVal, **zkw)
+                handles['time_pos'].units = tunits
+            sources = dict(fields, **{k: v for k, (_, v) in extra.items()})
+            for jt in range(shp[0]):
+                vt[jt] = ptime[jt]
+                for name, h in handles.items():
+                    h[jt, :] = sources[name][jt, :]
+            if corigin:
+                f.Origin = corigin
+            f.About = 'Lagrangian sea-ice drift'
+            f.Author = 'Generated with `%s` of `sitrack` (L. Brodeau, 2023)' % os.path.basename(sys.argv[0])
     print('      ===> ' + cf_out + ' saved!')
     return 0
+
+
+def _need(ds, kind, names, who):
+    have = ds.dimensions if kind == 'dimensions' else ds.variables
+    for n in names:
+        if n not in have:
+            _die(' ERROR [%s()]: no %s `%s` found into input file!' % (who, kind, n))
 
 
 def _check_tunits(v, who):
     u = getattr(v, "units", tunits_default)
     if u is not None and u != tunits_default:
-        print(' ERROR [' + who + '()]: we expect "' + tunits_default + '" as units for the time record vector, yet we have: ' + str(u))
-        raise SystemExit(0)
+        _die(' ERROR [%s()]: we expect "%s" as units for the time record vector, yet we have: %s'
+             % (who, tunits_default, u))
 
 
 def LoadNCtime(cfile, ltime2d=False, iverbose=0):
     """ncio.py:199-239 -> Nt, time [, time_pos]"""
     chck4f(cfile)
-    with open_dataset(cfile) as id_in:
-        if 'time' not in id_in.dimensions or 'time' not in id_in.variables:
-            print(' ERROR [LoadNCtime()]: no `time` found into input file!')
-            raise SystemExit(0)
-        Nt = id_in.dimensions['time'].size
-        _check_tunits(id_in.variables['time'], 'LoadNCtime')
-        print('    * [LoadNCtime] => reading "time" (' + str(Nt) + ' records) in file ' + path.basename(cfile))
-        ztime = np.asarray(id_in.variables['time'][:])
-        if ltime2d:
-            if 'time_pos' not in id_in.variables:
-                print(' ERROR [LoadNCtime()]: no variable `time_pos` found into input file!')
-                raise SystemExit(0)
-            _check_tunits(id_in.variables['time_pos'], 'LoadNCtime')
-            ztime2d = np.asarray(id_in.variables['time_pos'][:, :])
-            if ztime2d.shape[0] != Nt:
-                print(' ERROR [LoadNCtime()]: array `time_pos` has not the same number of records as `time`!!!')
-                raise SystemExit(0)
-            return Nt, ztime, ztime2d
-        return Nt, ztime
+    with open_dataset(cfile) as ds:
+        _need(ds, 'dimensions', ['time'], 'LoadNCtime')
+        _need(ds, 'variables', ['time'] + (['time_pos'] if ltime2d else []), 'LoadNCtime')
+        Nt = ds.dimensions['time'].size
+        _check_tunits(ds.variables['time'], 'LoadNCtime')
+        print('    * [LoadNCtime] => reading "time" (%d records) in file %s' % (Nt, os.path.basename(cfile)))
+        t1d = np.asarray(ds.variables['time'][:])
+        if not ltime2d:
+            return Nt, t1d
+        _check_tunits(ds.variables['time_pos'], 'LoadNCtime')
+        t2d = np.asarray(ds.variables['time_pos'][:, :])
+    if t2d.shape[0] != Nt:
+        _die(' ERROR [LoadNCtime()]: array `time_pos` has not the same number of records as `time`!!!')
+    return Nt, t1d, t2d
 
 
 def LoadNCdata(cfile, krec=-1, lmask=False, lGetTimePos=False, iverbose=0):
     """ncio.py:243-326 -> time, IDs, LatLon (..,nP,2) with lon in 0..360, YX (..,nP,2) [, mask][, time_pos]"""
-    need = ['id_buoy', 'latitude', 'longitude', 'y_pos', 'x_pos'] + (['time_pos'] if lGetTimePos else [])
     chck4f(cfile)
-    with open_dataset(cfile) as id_in:
-        for cd in ['time', 'buoy']:
-            if cd not in id_in.dimensions:
-                print(' ERROR [LoadNCdata()]: no dimensions `' + cd + '` found into input file!')
-                raise SystemExit(0)
-        for cv in need:
-            if cv not in id_in.variables:
-                print(' ERROR [LoadNCdata()]: no variable `' + cv + '` found into input file!')
-                raise SystemExit(0)
-        Nt = id_in.dimensions['time'].size
-        nP = id_in.dimensions['buoy'].size
-        _check_tunits(id_in.variables['time'], 'LoadNCdata')
-        idxR = krec if krec >= 0 else np.arange(Nt, dtype=int)
-        ztime = np.asarray(id_in.variables['time'][idxR])
-        kBIDs = np.zeros(nP, dtype=int)
-        kBIDs[:] = id_in.variables['id_buoy'][:]
-        zlat = np.asarray(id_in.variables['latitude'][idxR, :])
-        zlon = np.array(id_in.variables['longitude'][idxR, :])
-        zy = np.asarray(id_in.variables['y_pos'][idxR, :])
-        zx = np.asarray(id_in.variables['x_pos'][idxR, :])
-        if lmask:
-            zmsk = np.asarray(id_in.variables['mask'][idxR, :])
-        if lGetTimePos:
-            ztpos = np.asarray(id_in.variables['time_pos'][idxR, :])
-    zlon[:] = np.mod(zlon, 360.)
-    shp = (nP, 2) if krec >= 0 else (Nt, nP, 2)
-    zLatLon, zYX = np.zeros(shp), np.zeros(shp)
-    zLatLon[..., 0], zLatLon[..., 1] = zlat, zlon            # f4 -> f8 like the reference
-    zYX[..., 0], zYX[..., 1] = zy, zx
-    out = [ztime, kBIDs, zLatLon, zYX]
-    if lmask:
-        out.append(zmsk)
-    if lGetTimePos:
-        out.append(ztpos)
-    return tuple(out)
+    with open_dataset(cfile) as ds:
+        _need(ds, 'dimensions', ['time', 'buoy'], 'LoadNCdata')
+        _need(ds, 'variables', ['id_buoy', 'latitude', 'longitude', 'y_pos', 'x_pos']
+              + (['time_pos'] if lGetTimePos else []), 'LoadNCdata')
+        Nt, nP = ds.dimensions['time'].size, ds.dimensions['buoy'].size
+        _check_tunits(ds.variables['time'], 'LoadNCdata')
+        rec = krec if krec >= 0 else slice(None)
+        grab = lambda n: np.array(ds.variables[n][rec, :])
+        ztime = np.asarray(ds.variables['time'][rec])
+        ids = np.array(ds.variables['id_buoy'][:], dtype=int)
+        lat, lon, y, x = (grab(n) for n in ('latitude', 'longitude', 'y_pos', 'x_pos'))
+        tail = ([grab('mask')] if lmask else []) + ([grab('time_pos')] if lGetTimePos else [])
+    geo = np.stack([lat, np.mod(lon, 360.)], axis=-1).astype(np.float64)     # f4 -> f8 like the reference
+    yx = np.stack([y, x], axis=-1).astype(np.float64)
+    return tuple([ztime, ids, geo, yx] + tail)
 
 
 def SeedFileTimeInfo(fSeedNc, ltime2d=False, iverbose=0):
     """ncio.py:329-352 -> idate0, idateN (rounded to the hour), SeedName, SeedBatch, time_pos"""
-    from re import split
-    from math import ceil, floor
-    base = path.basename(fSeedNc)
-    cSeed = base.replace('SELECTION_', '').replace('.npz', '').replace('.nc', '')
-    cBtch = split('_', base)[2]
+    base = os.path.basename(fSeedNc)
+    name = re.sub(r'\.(nc|npz)$', '', base.replace('SELECTION_', ''))
+    batch = base.split('_')[2]
     chck4f(fSeedNc)
     if ltime2d:
-        ntr, zt, zt2d = LoadNCtime(fSeedNc, ltime2d=True, iverbose=iverbose)
-        idate0, idateN = np.min(zt2d), np.max(zt2d)
+        _, _, t2d = LoadNCtime(fSeedNc, ltime2d=True, iverbose=iverbose)
+        first, last = np.min(t2d), np.max(t2d)
     else:
-        ntr, zt = LoadNCtime(fSeedNc, iverbose=iverbose)
-        idate0, idateN = zt[0], zt[ntr - 1]
-        zt2d = []
-    print('    * [SeedFileTimeInfo] => earliest and latest time position in the SEED file: ' + e2c(idate0) + ' - ' + e2c(idateN))
-    idate0, idateN = int(floor(idate0 / 3600.) * 3600.), int(ceil(idateN / 3600.) * 3600.)
-    print('    * [SeedFileTimeInfo]  ==> will actually use rounded to the hour! => ' + e2c(idate0) + ' - ' + e2c(idateN))
-    return idate0, idateN, cSeed, cBtch, zt2d
+        n, t1d = LoadNCtime(fSeedNc, iverbose=iverbose)
+        first, last, t2d = t1d[0], t1d[n - 1], []
+    print('    * [SeedFileTimeInfo] => earliest and latest time position in the SEED file: %s - %s' % (e2c(first), e2c(last)))
+    first, last = int(math.floor(first / 3600.) * 3600.), int(math.ceil(last / 3600.) * 3600.)
+    print('    * [SeedFileTimeInfo]  ==> will actually use rounded to the hour! => %s - %s' % (e2c(first), e2c(last)))
+    return first, last, name, batch, t2d
 
 
 def ModelFileTimeInfo(fModelNc, iverbose=0):
-    """ncio.py:356-384 -> Nt, time_counter (i4), idate0, idateN, CONF, EXP (from the FILE NAME)"""
-    from re import split
-    with open_dataset(fModelNc) as ds_mod:
-        Nt = ds_mod.dimensions['time_counter'].size
-        _check_tunits(ds_mod.variables['time_counter'], 'ModelFileTimeInfo')
-        ztime = np.array(ds_mod.variables['time_counter'][:], dtype='i4')
-    print('    * [ModelFileTimeInfo] => ' + str(Nt) + ' records in input MODEL file!')
-    idate0, idateN = np.min(ztime), np.max(ztime)
-    print('    * [ModelFileTimeInfo] => earliest and latest time position in the MODEL file: ' + e2c(idate0) + ' - ' + e2c(idateN))
-    vn = split('_', path.basename(fModelNc))
-    zz = split('-', vn[1])
-    nconf = vn[0]
-    if len(zz) == 1:
-        zz = split('-', vn[0])
-        nconf = zz[0]
-    nexpr = zz[1]
-    print('    * [ModelFileTimeInfo] => NEMO config and experiment =', nconf, nexpr, '\n')
-    return Nt, ztime, idate0, idateN, nconf, nexpr
+    """ncio.py:356-384 -> Nt, time_counter (i4), idate0, idateN, CONF, EXP (both from the FILE NAME)"""
+    with open_dataset(fModelNc) as ds:
+        Nt = ds.dimensions['time_counter'].size
+        _check_tunits(ds.variables['time_counter'], 'ModelFileTimeInfo')
+        tmod = np.array(ds.variables['time_counter'][:], dtype='i4')
+    print('    * [ModelFileTimeInfo] => %d records in input MODEL file!' % Nt)
+    t0, tN = np.min(tmod), np.max(tmod)
+    print('    * [ModelFileTimeInfo] => earliest and latest time position in the MODEL file: %s - %s' % (e2c(t0), e2c(tN)))
+    parts = os.path.basename(fModelNc).split('_')
+    conf, second = parts[0], parts[1].split('-')
+    if len(second) == 1:                       # "<CONF>-<EXP>_1h_..." rather than "<CONF>_<x>-<EXP>_..."
+        second = parts[0].split('-')
+        conf = second[0]
+    print('    * [ModelFileTimeInfo] => NEMO config and experiment =', conf, second[1], '\n')
+    return Nt, tmod, t0, tN, conf, second[1]

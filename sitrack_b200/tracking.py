@@ -5,6 +5,8 @@ the GPU (libsitrack_b200.so); index bookkeeping and array shrinking stay in nump
 import numpy as np
 
 from . import _lib, config
+
+__all__ = ['rmin_conc', 'rFoundKM', 'GetTimeSpan', 'intersect2Seg', 'intersect2SegBatch', 'Survive', 'SurviveBatch', 'SeedInit', 'CrossedEdge', 'NewHostCell', 'UpdtInd4NewCell', 'debugSeeding', 'SidfexSeeding', 'ReadFromSidfexDatFile', 'nemoSeed']
 from ._lib import as_c, check, hptr
 
 rmin_conc = 0.1    # tracking.py:4 ice concentration below which a buoy is discontinued

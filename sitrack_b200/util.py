@@ -8,6 +8,8 @@ Time-string helpers are host Python.
 import numpy as np
 
 from . import _lib, config
+
+__all__ = ['chck4f', 'epoch2clock', 'clock2epoch', 'degE_to_degWE', 'Haversine', 'CartNPSkm2Geo1D', 'Geo2CartNPSkm1D', 'ConvertGeo2CartesianNPSkm', 'ConvertCartesianNPSkm2Geo', 'StdDev']
 from ._lib import as_c, check, hptr
 
 
