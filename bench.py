@@ -240,6 +240,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     ms, bsteps = timed_steps(K, W)
+    gpu_launches = launches["n"]                      # k_advect_step launches inside the timed region
     sampler.stop()
     clocks = sampler.summary()
 
@@ -382,7 +383,7 @@ def run_ours(args):
                                 "through, %d resident records (%.0f MB) are cycled; no flush"
                                 % (nP * B_ALG / 1e6, R, R * 3 * Nj * Ni * 4 / 1e6),
                           "parallelism": "buoys sharded over %d GPU(s), record replicated" % world},
-               "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["n"],
+               "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
                "clocks": clocks, "seed_locate": {"buoys_per_s": SC_t.shape[0] / (seed_ms * 1e-3), "ms": round(seed_ms, 3)}}
         out.update(extra)
         print(json.dumps(out), flush=True)
