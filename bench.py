@@ -26,6 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+SEED_BOX = int(os.environ.get("SITRACK_BENCH_SEED_BOX", "0")) or None   # diagnostic only
 B_ALG = 83.0          # algorithmic bytes per buoy-step: 25 state in + 25 out + 33 row
 D2H_PER_BUOY = 33     # y,x f8 + lat,lon f8 + mask i1
 WORKLOADS = {
@@ -126,7 +127,7 @@ def build_workload(name, rank, want_latlon_grid=True, n_dense=None):
     g = synth.make_grid(**synth.GRID_PRESETS[w["grid"]], seed=0, with_latlon=want_latlon_grid)
     U, V, IC = synth.make_records(g, w["nrec_res"], seed=1)
     if w["kind"] == "dense":
-        ids, SG, SC = synth.dense_seeds(g, n_dense or w["buoys"], IC[0], seed=3 + rank, with_latlon=False)
+        ids, SG, SC = synth.dense_seeds(g, n_dense or w["buoys"], IC[0], seed=3 + rank, with_latlon=False, box=SEED_BOX)
     elif w["kind"] == "hss5":
         ids, SG, SC = synth.hss_seeds(g, IC[0], khss=5)
     else:
@@ -214,13 +215,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def ll_of(b):                    # --no-latlon: diagnostic run without the lat/lon row (not a bench value)
+        return None if args.no_latlon else o_ll[b]
+
     def timed_steps(nsteps, nwarm, after_step=None):
         """-> (ms, alive buoy-steps in the timed part).  after_step(k, buf) may enqueue extra work."""
         reset()
         na = torch.zeros((nwarm + nsteps,), dtype=torch.int64, device=dev)
         for k in range(nwarm):
             b = k % NB
-            eng.step(k % R, k, o_yx[b], o_ll[b], o_mk[b], na[k:k + 1], stream)
+            eng.step(k % R, k, o_yx[b], ll_of(b), o_mk[b], na[k:k + 1], stream)
             if after_step:
                 after_step(k, b)
         barrier()
@@ -228,7 +232,7 @@ def run_ours(args):
         t0.record(stream)
         for k in range(nwarm, nwarm + nsteps):
             b = k % NB
-            eng.step(k % R, k, o_yx[b], o_ll[b], o_mk[b], na[k:k + 1], stream)
+            eng.step(k % R, k, o_yx[b], ll_of(b), o_mk[b], na[k:k + 1], stream)
             if after_step:
                 after_step(k, b)
         t1.record(stream)
@@ -557,6 +561,7 @@ def main():
     ap.add_argument("--workload", default="cfg5", choices=list(WORKLOADS))
     ap.add_argument("--kernel", default="tuned", help="k_advect_step variant: tuned, v1, or an integer launch-bound experiment")
     ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--no-latlon", action="store_true", help="diagnostic: skip the lat/lon row in the value loop")
     ap.add_argument("--multi", type=int, default=0, help="also time k_advect_multi with this many records per launch")
     ap.add_argument("--no-allgather", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -17,10 +17,21 @@ namespace st {
 // A point of the km plane, stored [y, x] like every coordinate pair upstream.
 struct __align__(16) pt { double y, x; };
 
+// Geometry gathers carry an L2 evict_last policy: ~1 GB of touch-once state and rows streams through
+// the 126 MB L2 every launch, and without the hint the cell geometry (re-used by the next record) is
+// evicted and every warp's first gather pays an HBM round trip.
+__device__ __forceinline__ unsigned long long l2_keep_policy()
+{
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ pt ldg_pt(const pt* __restrict__ a, int idx)
 {
-    const double2 v = __ldg(reinterpret_cast<const double2*>(a) + idx);
-    pt r; r.y = v.x; r.x = v.y; return r;
+    pt r;
+    asm("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+        : "=d"(r.y), "=d"(r.x) : "l"(a + idx), "l"(l2_keep_policy()));
+    return r;
 }
 // streaming (touch-once) accesses: keep them out of the way of the resident
 // geometry / velocity record in L1 and L2

@@ -45,13 +45,16 @@ def scattered_seeds(grid, n, seed=2):
     return _pack(lat, lon, y, x)
 
 
-def dense_seeds(grid, n, ic0, seed=3, jitter=0.42, f4=False, with_latlon=True):
+def dense_seeds(grid, n, ic0, seed=3, jitter=0.42, f4=False, with_latlon=True, box=None):
     """n buoys over the pack: random ocean T-cells with siconc>=0.9, jittered
     inside the cell, returned sorted by (j,i) (HSS1-with-replicas style)."""
     rng = np.random.default_rng(seed)
     Nj, Ni = grid["Nj"], grid["Ni"]
     m = grid["tmask"].astype(bool) & (ic0 >= 0.9)
     m[:3, :] = False; m[-3:, :] = False; m[:, :3] = False; m[:, -3:] = False
+    if box:                      # diagnostic: confine the cloud to a centred box of `box` x `box` cells
+        keep = np.zeros_like(m); j0, i0 = Nj // 2 - box // 2, Ni // 2 - box // 2
+        keep[j0:j0 + box, i0:i0 + box] = True; m &= keep
     cells = np.flatnonzero(m)
     pick = np.sort(rng.choice(cells, size=n, replace=n > cells.size))
     jj, ii = np.divmod(pick, Ni)

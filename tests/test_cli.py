@@ -83,3 +83,27 @@ def test_cli_full_run_vs_oracle(tmp_path, monkeypatch):
     quiet(cli.main)
     z2 = np.load(tmp_path / "nc" / out[0])
     assert np.array_equal(z2["y_pos"], z["y_pos"])
+
+
+@pytest.mark.gpu
+def test_readme_workflow_seeding_then_tracking(tmp_path, monkeypatch):
+    """The README workflow of the reference, end to end on synthetic files: generate the seeding file
+    from the mesh_mask + SI3 file (nemoSeed, HSS5), then track it with the CLI."""
+    import si3_part_tracker as cli
+    import generate_seeding
+    import synth
+    from make_synth_case import write_case
+    r = write_case(str(tmp_path / "in"), grid="small", nrec=12, hss=5)
+    monkeypatch.chdir(tmp_path)
+    fseed = quiet(generate_seeding.main, ["-d", "1996-12-15_00:00:00", "-m", r["mesh"], "-i", r["si3"], "-k", "0", "-S", "5"])
+    assert fseed == "./nc/sitrack_seeding_nemoTsi3_19961215_00_HSS5.npz"
+    z = np.load(fseed)
+    ids, SG, SC = synth.hss_seeds(r["grid"], r["records"][2][0], khss=5)
+    assert z["id_buoy"].shape == ids.shape and z["latitude"].dtype == np.float32
+    assert np.abs(z["latitude"][0] - SG[:, 0]).max() < 1e-5 and np.abs(z["y_pos"][0] - SC[:, 0]).max() < 1e-3
+    monkeypatch.setattr(sys, "argv", ["si3_part_tracker.py", "-i", r["si3"], "-m", r["mesh"], "-s", fseed, "-F", "-N", "SYNTH4"])
+    quiet(cli.main)
+    out = [f for f in os.listdir(tmp_path / "nc") if "_tracking_" in f]
+    assert len(out) == 1
+    t = np.load(tmp_path / "nc" / out[0])
+    assert t["y_pos"].shape[0] == 13 and t["mask"][0].all() and 0 < t["mask"][-1].sum() <= t["mask"].shape[1]
