@@ -55,10 +55,11 @@ int  st_create(st_ctx **out, int device, int Nj, int Ni,
                int uv_strategy, double rdt, double rmin_conc);
 void st_destroy(st_ctx *ctx);
 
-/* Step-kernel variant, all bit-identical in their results: 0 (default) tuned k_advect_step
- * (128 threads x 10 blocks/SM); 1 k_advect_step_v1, the straightforward kernel kept as A/B
- * reference (also SITRACK_B200_KERNEL=v1); 4 / 9 the tuned kernel at 128x8 / 256x4;
- * 8 k_advect_pipe, the persistent TMA + cp.async pipelined form.                          */
+/* Step-kernel variant, all bit-identical in their results:
+ *   0 (default) k_advect_persist 64x16: tuned step as persistent CTAs with a cross-tile walk queue;
+ *   7 the same at 128x8;  4 / 9 k_advect_step, the tuned step with one block per tile (128x10 / 256x4);
+ *   1 k_advect_step_v1, the straightforward kernel (also SITRACK_B200_KERNEL=v1);
+ *   8 k_advect_pipe, persistent CTAs with a TMA state ring and cp.async gathers.               */
 int  st_set_kernel_variant(st_ctx *ctx, int variant);
 
 /* Polar-stereographic parameters of CartNPSkm2Geo1D (util.py:413: lat0=70, lon0=-45). */
@@ -163,6 +164,10 @@ int  st_survive(int device, int64_t n, const int32_t *ji, int Nj, int Ni, const 
                 const double *ic5, double rmin_conc, int32_t *kill);
 int  st_haversine(int device, int64_t n, double plat, double plon, const double *lat, const double *lon,
                   double *out_km);
+
+/* Diagnostics: the step kernel's own inverse projection (polynomial latitude above ~37N, table-
+ * driven angles), host in/out like st_xy2latlon; tests compare it with the accurate kernel.   */
+int  st_selftest_xy2latlon_fast(int device, int64_t n, const double *yx, double *latlon, double lat_ts, double lon0);
 
 /* Diagnostics: the step kernel divides displacements by 1000 (si3_part_tracker.py:457-458)
  * with a reciprocal + exact-residual sequence; q_fast is that result, q_div the IEEE

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libsitrack_b200.so")
+SO_PATH = os.environ.get("SITRACK_B200_LIB") or os.path.join(HERE, "libsitrack_b200.so")   # env: A/B builds
 
 ST_OK, ST_EINVAL, ST_ECUDA, ST_ESTATE, ST_ENOMEM = 0, -1, -2, -3, -4
 
@@ -30,6 +30,7 @@ SIGNATURES = {
     "st_destroy": (None, [vp]),
     "st_set_projection": (c_int, [vp, c_dbl, c_dbl]),
     "st_set_kernel_variant": (c_int, [vp, c_int]),
+    "st_selftest_xy2latlon_fast": (c_int, [c_int, c_i64, vp, vp, c_dbl, c_dbl]),
     "st_selftest_div1000": (c_int, [c_int, c_i64, vp, vp, vp]),
     "st_selftest_divide": (c_int, [c_int, c_i64, vp, vp, vp, vp]),
     "st_set_locate_grid": (c_int, [vp, vp, vp, vp]),

@@ -39,11 +39,12 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: experimental A/B builds (`python -m sitrack_b200.build -DNAME=V -o path.so`)."""
+    if not force and not stale() and not out:
         return SO
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", SO] + [os.path.join(CSRC, f) for f in SOURCES]
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
+          ["-o", out or SO] + [os.path.join(CSRC, f) for f in SOURCES]
     env = dict(os.environ)
     # an env CC/CXX may point at a wrapper; let nvcc use the system g++
     if os.path.exists("/usr/bin/g++"):
@@ -53,8 +54,10 @@ def build(force=False, verbose=False):
         sys.stderr.write(r.stdout)
     if r.returncode:
         raise RuntimeError("nvcc failed (%d)" % r.returncode)
-    return SO
+    return out or SO
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    outp = sys.argv[sys.argv.index("-o") + 1] if "-o" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outp))

@@ -73,6 +73,42 @@ static double proj_akm1(double lat_ts_deg, double e)
     return cos(phits) / ts / sqrt(1.0 - es * es);
 }
 
+// Geodetic latitude as a function of t = tan(pi/4 - chi/2) on 0 <= t <= 1/2 (lat >~ 37N):
+// phi - pi/2 is odd in t, so phi = pi/2 + t Q(w), w = 8 t^2 - 1 in [-1,1].  Q is analytic with its
+// nearest singularity at w = -9, so its Chebyshev coefficients fall like 17.9^-k: degree 11 leaves
+// < 1e-15.  Coefficient generation (host, long double), like the angle table: not tracking arithmetic.
+static void fit_lat_poly(double e_, double out[12])
+{
+    const int N = 12, M = 32;
+    const long double e = e_, PI_L = 3.14159265358979323846264338327950288L;
+    long double c[N] = {0};
+    for (int j = 0; j < M; ++j) {
+        const long double th = PI_L * (j + 0.5L) / M, w = cosl(th);
+        const long double t = sqrtl((w + 1.0L) / 8.0L);
+        long double phi = PI_L / 2 - 2 * atanl(t);
+        for (int it = 0; it < 60; ++it) {
+            const long double es = e * sinl(phi);
+            phi = PI_L / 2 - 2 * atanl(t * powl((1 - es) / (1 + es), e / 2));
+        }
+        const long double f = (phi - PI_L / 2) / t;
+        for (int k = 0; k < N; ++k) c[k] += f * cosl(k * th);
+    }
+    for (int k = 0; k < N; ++k) c[k] *= 2.0L / M;
+    c[0] *= 0.5L;
+    // Chebyshev -> monomial: T_0 = 1, T_1 = w, T_{k+1} = 2 w T_k - T_{k-1}
+    long double a[N] = {0}, Tkm1[N] = {0}, Tk[N] = {0};
+    Tkm1[0] = 1; Tk[1] = 1;
+    a[0] += c[0];
+    for (int i = 0; i < N; ++i) a[i] += c[1] * Tk[i];
+    for (int k = 2; k < N; ++k) {
+        long double Tn[N] = {0};
+        for (int i = 0; i < N; ++i) { Tn[i] = -Tkm1[i]; if (i > 0) Tn[i] += 2 * Tk[i - 1]; }
+        for (int i = 0; i < N; ++i) a[i] += c[k] * Tn[i];
+        for (int i = 0; i < N; ++i) { Tkm1[i] = Tk[i]; Tk[i] = Tn[i]; }
+    }
+    for (int k = 0; k < N; ++k) out[k] = (double)a[k];
+}
+
 static ProjConst make_proj(double lat_ts, double lon0)
 {
     const double es = kF * (2.0 - kF), e = sqrt(es);
@@ -87,6 +123,8 @@ static ProjConst make_proj(double lat_ts, double lon0)
     p.c[4] = 4174. / 315 * n5 - 144838. / 6237 * n6;
     p.c[5] = 601676. / 22275 * n6;
     p.lon0_rad = lon0 * 0.017453292519943295;
+    p.fill_lat = p.fill_lon = 0.0;
+    fit_lat_poly(e, p.lat_poly);
     return p;
 }
 static ProjFwdConst make_proj_fwd(double lat_ts, double lon0)
@@ -213,7 +251,7 @@ int st_create(st_ctx** out, int device, int Nj, int Ni, const double* Yf, const 
 
 int st_set_kernel_variant(st_ctx* c, int variant)
 {
-    if (!c || variant < 0 || variant > 9 || variant == 2 || variant == 3 || (variant >= 5 && variant <= 7)) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 tuned, 1 v1, 4/9 other launch shapes, 8 pipelined");
+    if (!c || variant < 0 || variant > 9 || variant == 2 || variant == 3 || variant == 5 || variant == 6) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 persistent tuned (default), 1 v1, 4/9 one-block-per-tile tuned, 7 persistent 128x8, 8 TMA pipelined");
     c->variant = variant;
     return ST_OK;
 }
@@ -594,6 +632,19 @@ int st_xy2latlon_dev(int64_t n, const double* yx, double* latlon, double lat_ts,
 {
     if (n < 0 || !yx || !latlon) return fail(nullptr, ST_EINVAL, "st_xy2latlon_dev: NULL argument");
     CUS(launch_xy2latlon((const pt*)yx, (pt*)latlon, n, make_proj(lat_ts, lon0), (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_selftest_xy2latlon_fast(int device, int64_t n, const double* yx, double* latlon, double lat_ts, double lon0)
+{
+    if (n < 0 || !yx || !latlon) return fail(nullptr, ST_EINVAL, "st_selftest_xy2latlon_fast: NULL argument");
+    int rc = use_device(nullptr, device); if (rc) return rc;
+    if (n == 0) return ST_OK;
+    Scratch s; double *a, *b; AngEntry* tab = nullptr;
+    CUS(s.up(&a, yx, (size_t)2 * n)); CUS(s.alloc(&b, (size_t)2 * n));
+    CUS(make_angle_table(&tab)); s.p.push_back(tab);
+    CUS(launch_xy2latlon_fast((const pt*)a, (pt*)b, n, make_proj(lat_ts, lon0), tab, 0));
+    CUS(cudaMemcpy(latlon, b, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
     return ST_OK;
 }
 

@@ -135,6 +135,7 @@ struct ProjConst {
     double c[6];       // series coefficients of sin(2k chi), k = 1..6
     double lon0_rad;   // central longitude
     double fill_lat, fill_lon;   // inv_stere of (-9999,-9999) km: what rows of idle buoys hold (:493)
+    double lat_poly[12];         // phi = pi/2 + t * sum_k lat_poly[k] (8 t^2 - 1)^k for t <= 1/2
 };
 
 __device__ __forceinline__ pt inv_stere(pt yx, const ProjConst& pc)
@@ -164,21 +165,22 @@ __device__ __forceinline__ pt inv_stere(pt yx, const ProjConst& pc)
 // m cos(alpha_j) - M sin(alpha_j) and a 4-term asin series (error < 1e-19 rad).
 struct __align__(16) AngEntry { double alpha, ca, sa, pad; };
 
+// One Newton step on the MUFU seeds (~2^-20): relative error ~1e-12.  Enough here: both angle
+// evaluations are direction-only (a common scale error of sin and cos cancels), and the error of
+// t = rho * k_t moves the latitude by 2 t eps <= 1e-12 rad = 6e-11 degrees.
 __device__ __forceinline__ double rcp_nr(double d)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    double e = fma(-d, y, 1.0); y = fma(y, e, y);
-    e = fma(-d, y, 1.0);        y = fma(y, e, y);
-    return y;
+    const double e = fma(-d, y, 1.0);
+    return fma(y, e, y);
 }
 __device__ __forceinline__ double rsqrt_nr(double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-(x * y), y, 1.0); y = fma(0.5 * y, e, y);
-    e = fma(-(x * y), y, 1.0);        y = fma(0.5 * y, e, y);
-    return y;
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(0.5 * y, e, y);
 }
 __device__ __forceinline__ double angle_of_unit(double s, double c, const AngEntry* __restrict__ tab)
 {
@@ -201,21 +203,32 @@ __device__ __forceinline__ double angle_of_unit(double s, double c, const AngEnt
 
 __device__ __forceinline__ pt inv_stere_fast(pt yx, const ProjConst& pc, const AngEntry* __restrict__ tab)
 {
-    const double PI = 3.141592653589793, R2D = 57.29577951308232;
+    const double HALFPI = 1.5707963267948966, PI = 3.141592653589793, R2D = 57.29577951308232;
     const double r2 = fma(yx.x, yx.x, yx.y * yx.y);
     const double rinv = (r2 > 0.0) ? rsqrt_nr(r2) : 0.0;          // pole: lam = 0 like PROJ
     const double t = (r2 * rinv) * pc.k_t;
     const double t2 = t * t;
-    const double inv = rcp_nr(1.0 + t2);
-    const double s = (1.0 - t2) * inv;              // sin(chi)
-    const double c = (t + t) * inv;                 // cos(chi)
-    const double chi = angle_of_unit(s, c, tab);
-    const double s2 = (s + s) * c;                  // sin(2 chi)
-    const double c2x2 = fma(-4.0 * s, s, 2.0);      // 2 cos(2 chi)
-    double b2 = 0.0, b1 = pc.c[4];                  // c[5] = 6e-16 rad is dropped
+    double phi;
+    if (t2 <= 0.25) {
+        // latitudes above ~37N: phi - pi/2 is odd in t, phi = pi/2 + t Q(8 t^2 - 1) with Q a degree-11
+        // polynomial fitted at st_create for the ellipsoid (|error| < 1e-14 rad, see make_proj)
+        const double w = fma(8.0, t2, -1.0);
+        double q = pc.lat_poly[11];
 #pragma unroll
-    for (int k = 3; k >= 0; --k) { const double b0 = fma(c2x2, b1, pc.c[k] - b2); b2 = b1; b1 = b0; }
-    const double phi = fma(b1, s2, chi);
+        for (int k = 10; k >= 0; --k) q = fma(q, w, pc.lat_poly[k]);
+        phi = fma(t, q, HALFPI);
+    } else {
+        const double inv = rcp_nr(1.0 + t2);
+        const double s = (1.0 - t2) * inv;              // sin(chi)
+        const double c = (t + t) * inv;                 // cos(chi)
+        const double chi = angle_of_unit(s, c, tab);
+        const double s2 = (s + s) * c;                  // sin(2 chi)
+        const double c2x2 = fma(-4.0 * s, s, 2.0);      // 2 cos(2 chi)
+        double b2 = 0.0, b1 = pc.c[4];                  // c[5] = 6e-16 rad is dropped
+#pragma unroll
+        for (int k = 3; k >= 0; --k) { const double b0 = fma(c2x2, b1, pc.c[k] - b2); b2 = b1; b1 = b0; }
+        phi = fma(b1, s2, chi);
+    }
     double lam = angle_of_unit(yx.x * rinv, -(yx.y * rinv), tab) + pc.lon0_rad;
     if (lam > PI) lam -= 2.0 * PI;
     if (lam < -PI) lam += 2.0 * PI;

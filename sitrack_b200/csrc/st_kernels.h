@@ -46,6 +46,7 @@ cudaError_t launch_advect_multi(const AdvectGrid& g, const float* rec0, long lon
                                 const BuoyState& s, int jrec0, const StepOut& o, long long out_stride,
                                 cudaStream_t st);
 cudaError_t launch_xy2latlon(const pt* yx, pt* latlon, long long n, const ProjConst& pc, cudaStream_t st);
+cudaError_t launch_xy2latlon_fast(const pt* yx, pt* latlon, long long n, const ProjConst& pc, const AngEntry* tab, cudaStream_t st);
 cudaError_t launch_latlon2xy(const pt* latlon, pt* yx, long long n, const ProjFwdConst& pc, cudaStream_t st);
 
 // ---- locate (st_locate.cu) ---------------------------------------------------------

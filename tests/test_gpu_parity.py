@@ -129,7 +129,7 @@ def test_track_golden(torch, corc, gold_track, name, multi):
     assert np.abs(ll - want).max() < LATLON_TOL_DEG                  # also for the -9999 rows (:493)
 
 
-@pytest.mark.parametrize("variant", [1, 4, 8, 9])
+@pytest.mark.parametrize("variant", [1, 4, 7, 8, 9])
 @pytest.mark.parametrize("name", list(TRACK_CASES))
 def test_track_golden_other_kernels(torch, gold_track, name, variant):
     """v1 (straightforward), the other launch shapes of the tuned kernel and the persistent TMA/cp.async
@@ -307,7 +307,7 @@ def test_large_cloud_tuned_vs_v1_vs_oracle(torch, corc, preset, n, nrec, scale):
     ref = corc.track(g, U, V, IC, pos0, cell0.astype(np.int64), history=False)
     assert ref["ncross"] > 0.02 * ik.size * nrec and ref["alive"].sum() < ik.size
     dev = torch.device("cuda", 0)
-    for variant in (0, 1, 8):
+    for variant in (0, 1, 4, 8):
         with engine_for(g) as eng:
             eng.set_kernel_variant(variant)
             eng.set_buoys(pos0, cell0)
@@ -510,3 +510,24 @@ def test_fcc_golden(sit, gold_seed):
             ji, vr = sit.FCC((S["SG"][k, 0], S["SG"][k, 1]), g["latT"], g["lonT"], g["latF"], g["lonF"], cellType='T',
                              rd_found_km=2.5, resolkm=g["ResKM"], max_itr=10)
         assert list(ji) == list(S["fcc_ji"][n]) and np.array_equal(np.asarray(vr), S["fcc_vrt"][n])
+
+
+def test_fast_projection_all_latitudes(sit, corc):
+    """The step kernel's own inverse (polynomial latitude for t <= 1/2, table-driven angles, one-Newton
+    rcp/rsqrt) against the PROJ-style iteration: Arctic, mid-latitudes, southern hemisphere, the pole,
+    the axes and the fill point."""
+    from sitrack_b200 import _lib
+    rng = np.random.default_rng(44)
+    yx = np.concatenate([rng.uniform(-4500, 4500, (200_000, 2)),           # lat >~ 35N
+                         rng.uniform(-16000, 16000, (100_000, 2)),         # down to the southern hemisphere
+                         rng.uniform(-50, 50, (20_000, 2)),                # around the pole
+                         [[0.0, 0.0], [-9999.0, -9999.0], [0.0, 123.0], [123.0, 0.0], [-77.0, 0.0], [0.0, -5.0]]])
+    yx = np.ascontiguousarray(yx)
+    ll = np.empty_like(yx)
+    _lib.check(_lib.lib().st_selftest_xy2latlon_fast(0, yx.shape[0], yx.ctypes.data, ll.ctypes.data, 70.0, -45.0))
+    want = corc.inv_stere(yx)
+    dlon = np.abs(ll[:, 1] - want[:, 1]); dlon = np.minimum(dlon, 360.0 - dlon)      # +-180 are the same meridian
+    assert np.abs(ll[:, 0] - want[:, 0]).max() < LATLON_TOL_DEG
+    near_pole = np.hypot(yx[:, 0], yx[:, 1]) < 1e-6
+    assert dlon[~near_pole].max() < LATLON_TOL_DEG
+    assert ll[-6, 0] == 90.0 and ll[-6, 1] == -45.0                                     # the pole: lam = lon0 like PROJ
