@@ -43,6 +43,7 @@ def to_bytes(v, unit):
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
+    n_items = float(sys.argv[3]) if len(sys.argv) > 3 else None      # work items (buoys) per launch, for persistent kernels
     rows = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "raw", "--csv"]))))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ix = {k: i for i, k in enumerate(hdr)}
@@ -95,6 +96,8 @@ def main():
     if mix:
         tot = sum(mix.values())
         grid = launches[0].get("launch__grid_size", 0) * launches[0].get("launch__block_size", 0) / 32 or 1
+        if n_items:
+            grid = n_items / 32.0                       # "per warp" then means per 32 work items
         with open(out + "_opmix.csv", "w") as f:
             f.write("opcode,warp_instructions,percent,per_warp\n")
             for k, v in mix.most_common():
