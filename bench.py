@@ -320,56 +320,116 @@ def run_ours(args):
                               "bytes_per_rank_per_step": int(npad * 16), "what": "k_advect_step + NCCL "
                               "all_gather_into_tensor of (y,x) f8 per record on a side stream"}
 
+    # -- the same loop with the all-gather FUSED into the step kernel (stores into every rank's gathered
+    #    array over NVLink peer memory; st_step_gather) ---------------------------------------------
+    if world > 1 and not args.no_allgather:
+        cnt = torch.zeros((world,), dtype=torch.int64, device=dev)
+        cnt[rank] = nP
+        dist.all_reduce(cnt)
+        cnts = cnt.cpu().numpy()
+        offs = np.concatenate([[0], np.cumsum(cnts)])
+        for tag, f4 in (("allgather_fused", False), ("allgather_fused_f4", True)):
+            reset(); torch.cuda.synchronize()
+            hnd = eng.gather_create(rank, world, int(offs[-1]), int(offs[rank]), f4=f4, nbuf=NB)
+            mine = torch.tensor(list(hnd), dtype=torch.uint8, device=dev)
+            allh = torch.empty((world * 64,), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine)
+            eng.gather_connect_ipc(bytes(allh.cpu().numpy().tobytes()))
+            barrier()
+            cons = torch.cuda.Stream(dev)
+            Ka = max(4, min(K, 200)); Wa = min(W, 5)
+            na_g = torch.zeros((Wa + Ka,), dtype=torch.int64, device=dev)
+
+            def gsteps(k0, n):
+                for k in range(k0, k0 + n):
+                    b = k % NB
+                    eng.step_gather(k % R, k, b, k + 1, ll_of(b), o_mk[b], na_g[k:k + 1], stream)
+                    eng.gather_wait(k + 1, cons)        # the consumer stream sees the whole gathered row ...
+                    eng.gather_ack(k + 1, cons)         # ... and frees the buffer for sequence k + 1 + NB
+            gsteps(0, Wa)
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(stream)
+            gsteps(Wa, Ka)
+            t1.record(stream)
+            ec = torch.cuda.Event(enable_timing=True); ec.record(cons)
+            barrier()
+            ms_g = max(t0.elapsed_time(t1), t0.elapsed_time(ec))     # until the last row has LANDED here too
+            bad = eng.gather_timed_out()
+            ms_g, bs_g = reduce_max_sum(ms_g, int(na_g[Wa:].sum().item()))
+            extra[tag] = {"value": bs_g / (ms_g * 1e-3), "unit": "buoy-steps/s", "steps": Ka,
+                          "bytes_into_each_rank_per_step": int((offs[-1] - cnts[rank]) * (8 if f4 else 16)),
+                          "timed_out": bool(bad),
+                          "what": "k_advect_persist stores every new (y,x) %s into the gathered array of all %d ranks "
+                                  "itself (NVLink peer stores, ready/ack flags, no NCCL call)" % ("f4" if f4 else "f8", world)}
+            barrier()
+            eng.gather_destroy()
+            barrier()
+
     # -- e2e: host buffers in, host rows out, every step (pinned memory, 3 streams) ---------------
     Ke = args.e2e_steps if args.e2e_steps > 0 else max(4, min(K, 40 if nP > 2_000_000 else 200))
     h_rec = torch.from_numpy(np.stack([U, V, IC], axis=1).astype(np.float32)).pin_memory()   # (R,3,Nj,Ni)
-    h_yx = [torch.empty((nP, 2), dtype=torch.float64).pin_memory() for _ in range(NB)]
-    h_ll = [torch.empty((nP, 2), dtype=torch.float64).pin_memory() for _ in range(NB)]
-    h_mk = [torch.empty((nP,), dtype=torch.int8).pin_memory() for _ in range(NB)]
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     checksum = [0.0]
+    na_e = [None]
 
-    def e2e_loop(n, k0):
-        ev_in, ev_st, ev_out = {}, {}, {}
-        for k in range(k0, k0 + n):
-            b = k % 2
-            if k - 2 in ev_st:
-                s_in.wait_event(ev_st[k - 2])                       # device slot b free again
-            eng.upload_record(b, h_rec[k % R], s_in)                # H2D of this step's inputs
-            ev_in[k] = torch.cuda.Event(); ev_in[k].record(s_in)
-            stream.wait_event(ev_in[k])
-            if k - NB in ev_out:
-                stream.wait_event(ev_out[k - NB])                   # device out buffer b drained
-            eng.step(b, k, o_yx[b], o_ll[b], o_mk[b], na_e[k:k + 1], stream)
-            ev_st[k] = torch.cuda.Event(); ev_st[k].record(stream)
-            s_out.wait_event(ev_st[k])
-            if k - NB in ev_out:
-                ev_out[k - NB].synchronize()                        # host row buffer b consumed
-                checksum[0] += float(h_yx[b][0, 0])                 # the host reads the result
-            with torch.cuda.stream(s_out):
-                h_yx[b].copy_(o_yx[b], non_blocking=True)           # D2H of the trajectory row
-                h_ll[b].copy_(o_ll[b], non_blocking=True)
-                h_mk[b].copy_(o_mk[b], non_blocking=True)
-            ev_out[k] = torch.cuda.Event(); ev_out[k].record(s_out)
-        torch.cuda.synchronize()
+    def e2e_run(rdt):
+        """-> (seconds, alive buoy-steps) of Ke timed steps with rows of dtype rdt through host buffers."""
+        h_yx = [torch.empty((nP, 2), dtype=rdt).pin_memory() for _ in range(NB)]
+        h_ll = [torch.empty((nP, 2), dtype=rdt).pin_memory() for _ in range(NB)]
+        h_mk = [torch.empty((nP,), dtype=torch.int8).pin_memory() for _ in range(NB)]
+        d_yx = o_yx if rdt == torch.float64 else [torch.empty((nP, 2), dtype=rdt, device=dev) for _ in range(NB)]
+        d_ll = o_ll if rdt == torch.float64 else [torch.empty((nP, 2), dtype=rdt, device=dev) for _ in range(NB)]
 
-    reset(); eng.record_slots(max(R, 2))
-    na_e = torch.zeros((Ke + 3,), dtype=torch.int64, device=dev)
-    e2e_loop(min(3, Ke), 0)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(Ke, 3)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    e2e_bs = float(na_e[3:].sum().item())                           # alive buoys advanced in the timed steps
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev); s = torch.tensor([e2e_bs], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        e2e_s, e2e_bs = float(t.item()), float(s.item())
+        def e2e_loop(n, k0):
+            ev_in, ev_st, ev_out = {}, {}, {}
+            for k in range(k0, k0 + n):
+                b = k % 2
+                if k - 2 in ev_st:
+                    s_in.wait_event(ev_st[k - 2])                       # device slot b free again
+                eng.upload_record(b, h_rec[k % R], s_in)                # H2D of this step's inputs
+                ev_in[k] = torch.cuda.Event(); ev_in[k].record(s_in)
+                stream.wait_event(ev_in[k])
+                if k - NB in ev_out:
+                    stream.wait_event(ev_out[k - NB])                   # device out buffer b drained
+                eng.step(b, k, d_yx[b], d_ll[b], o_mk[b], na_e[0][k:k + 1], stream)
+                ev_st[k] = torch.cuda.Event(); ev_st[k].record(stream)
+                s_out.wait_event(ev_st[k])
+                if k - NB in ev_out:
+                    ev_out[k - NB].synchronize()                        # host row buffer b consumed
+                    checksum[0] += float(h_yx[b][0, 0])                 # the host reads the result
+                with torch.cuda.stream(s_out):
+                    h_yx[b].copy_(d_yx[b], non_blocking=True)           # D2H of the trajectory row
+                    h_ll[b].copy_(d_ll[b], non_blocking=True)
+                    h_mk[b].copy_(o_mk[b], non_blocking=True)
+                ev_out[k] = torch.cuda.Event(); ev_out[k].record(s_out)
+            torch.cuda.synchronize()
+
+        reset(); eng.record_slots(max(R, 2))
+        na_e[0] = torch.zeros((Ke + 3,), dtype=torch.int64, device=dev)
+        e2e_loop(min(3, Ke), 0)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(Ke, 3)
+        barrier()
+        sec = time.perf_counter() - t0
+        bs = float(na_e[0][3:].sum().item())                            # alive buoys advanced in the timed steps
+        if world > 1:
+            t = torch.tensor([sec], dtype=torch.float64, device=dev); s_ = torch.tensor([bs], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(s_, op=dist.ReduceOp.SUM)
+            sec, bs = float(t.item()), float(s_.item())
+        return sec, bs
+
+    e2e_s, e2e_bs = e2e_run(torch.float64)
     e2e = {"value": e2e_bs / e2e_s, "unit": "buoy-steps/s", "h2d_bytes_per_step": int(3 * Nj * Ni * 4),
            "d2h_bytes_per_step": int(D2H_PER_BUOY * nP), "steps": Ke, "ms_per_step": round(e2e_s / Ke * 1e3, 3),
            "what": "per record: pinned host u/v/siconc -> st_upload_record -> st_step -> trajectory row "
                    "(y,x,lat,lon f8 + mask) copied to pinned host memory and read"}
+    # the same through st_step_f4: rows in the dtype the reference's output files store (ncio.py:153-159)
+    f4_s, f4_bs = e2e_run(torch.float32)
+    extra["e2e_file_dtype_rows"] = {"value": f4_bs / f4_s, "unit": "buoy-steps/s", "h2d_bytes_per_step": int(3 * Nj * Ni * 4),
+                                    "d2h_bytes_per_step": int(17 * nP), "steps": Ke, "ms_per_step": round(f4_s / Ke * 1e3, 3),
+                                    "what": "as e2e, rows as (y,x,lat,lon) f4 + mask = the f8 rows cast to the output file's dtype on the device"}
 
     # -- CPU baseline on this box's host cores (rank 0, N=1 only) ---------------------------------
     cpu = None

@@ -35,7 +35,7 @@ extern "C" {
 #define ST_ESTATE   -3      /* call order (e.g. step before set_buoys)   */
 #define ST_ENOMEM   -4
 
-#define ST_ABI_VERSION 1
+#define ST_ABI_VERSION 2
 
 typedef struct st_ctx st_ctx;
 
@@ -57,7 +57,7 @@ void st_destroy(st_ctx *ctx);
 
 /* Step-kernel variant, all bit-identical in their results:
  *   0 (default) k_advect_persist 64x16: tuned step as persistent CTAs with a cross-tile walk queue;
- *   7 the same at 128x8;  4 / 9 k_advect_step, the tuned step with one block per tile (128x10 / 256x4);
+ *   7 / 10 / 11 the same at 128x8 / 64x18 / 64x20;  4 / 9 k_advect_step, the tuned step with one block per tile (128x10 / 256x4);
  *   1 k_advect_step_v1, the straightforward kernel (also SITRACK_B200_KERNEL=v1);
  *   8 k_advect_pipe, persistent CTAs with a TMA state ring and cp.async gathers.               */
 int  st_set_kernel_variant(st_ctx *ctx, int variant);
@@ -138,6 +138,59 @@ int  st_step_multi(st_ctx *ctx, const float *rec_dev, int64_t rec_stride, int nr
  * trajectory row in host arrays (any of them NULL to skip).  Synchronous.               */
 int  st_track_record_host(st_ctx *ctx, int jrec, const float *u, const float *v, const float *ic,
                           double *out_yx, double *out_latlon, int8_t *out_mask, int64_t *n_alive);
+
+/* ---- rows in the output file's dtype ----------------------------------------------------
+ * The reference keeps xPosC/xPosG as f8 in memory and casts to f4 when it writes the file
+ * (sitrack/ncio.py:153-159: every trajectory variable is created 'f4').  These variants
+ * write the trajectory row as (nP,2) f4 directly -- each value rounded once, to nearest even,
+ * exactly like that cast -- so a caller that only feeds the writer moves 17 B per buoy off
+ * the device instead of 33 B.  The buoy STATE stays f8 on the device; results of later
+ * records are unaffected.  Same arguments and behaviour as the f8 forms otherwise.          */
+int  st_step_f4(st_ctx *ctx, int slot, int jrec, float *out_yx_dev, float *out_latlon_dev,
+                int8_t *out_mask_dev, uint64_t *n_alive_dev, void *stream);
+int  st_step_multi_f4(st_ctx *ctx, const float *rec_dev, int64_t rec_stride, int nrec, int jrec0,
+                      float *out_yx_dev, float *out_latlon_dev, int8_t *out_mask_dev,
+                      int64_t out_stride, uint64_t *n_alive_dev, void *stream);
+int  st_track_record_host_f4(st_ctx *ctx, int jrec, const float *u, const float *v, const float *ic,
+                             float *out_yx, float *out_latlon, int8_t *out_mask, int64_t *n_alive);
+
+/* ---- fused per-record all-gather of positions over peer memory (multi-GPU) ----------------
+ * Buoys are sharded over ranks (one process per GPU; they never interact,
+ * si3_part_tracker.py:378-488).  When every rank needs the whole xPosC[jt+1] row, the step
+ * kernel itself stores each buoy's new position into the gathered (nP_total,2) array of EVERY
+ * rank -- its own HBM plus the peer-mapped HBM of the others over NVLink -- so the transfer
+ * overlaps the arithmetic thread by thread and no separate collective runs.
+ *
+ *   st_gather_create   allocates this rank's block (nbuf gathered arrays + a flag page) and
+ *                      returns its 64-byte CUDA IPC handle; call after st_set_buoys.  `offset`
+ *                      is the index of this rank's first buoy in the global order; f4 != 0
+ *                      gathers (nP_total,2) f4 instead of f8.
+ *   st_gather_connect_ipc   maps the other ranks' blocks; `handles` = world x 64 bytes in rank
+ *                      order (exchange them with any host-side all-gather).
+ *   st_gather_connect_ptrs  same for ranks living in ONE process (contexts on one device, or
+ *                      on devices with peer access enabled): `blocks` = world device pointers
+ *                      from st_gather_block.
+ *   st_step_gather     ASYNC: st_step whose yx row goes to buffer `buf` of every rank.  `seq`
+ *                      (1, 2, 3, ... per record) orders producers and consumers: before storing,
+ *                      the stream waits until every rank has acknowledged sequence seq - nbuf;
+ *                      after the kernel it releases ready[rank] = seq on every rank.
+ *   st_gather_wait     ASYNC: `stream` waits until the rows of sequence `seq` from ALL ranks
+ *                      have landed in this rank's buffer (st_gather_buffer).
+ *   st_gather_ack      ASYNC: tells every rank this one is done reading sequence `seq`.
+ *   st_gather_timed_out  1 if a device-side wait gave up after 10 s (a peer died); syncs.   */
+#define ST_IPC_HANDLE_BYTES 64
+int  st_gather_create(st_ctx *ctx, int rank, int world, int64_t nP_total, int64_t offset, int f4, int nbuf,
+                      void *handle_out);
+int  st_gather_connect_ipc(st_ctx *ctx, const void *handles);
+int  st_gather_connect_ptrs(st_ctx *ctx, void *const *blocks);
+int  st_gather_block(st_ctx *ctx, void **block_dev, int64_t *block_bytes);
+int  st_gather_buffer(st_ctx *ctx, int buf, void **gathered_dev);
+int  st_step_gather(st_ctx *ctx, int slot, int jrec, int buf, uint64_t seq, void *out_latlon_dev,
+                    int8_t *out_mask_dev, uint64_t *n_alive_dev, void *stream);
+int  st_gather_wait(st_ctx *ctx, uint64_t seq, void *stream);
+int  st_gather_ack(st_ctx *ctx, uint64_t seq, void *stream);
+int  st_gather_timed_out(st_ctx *ctx, int *timed_out);
+int  st_gather_destroy(st_ctx *ctx);
 
 /* ---- projections (util.py:394-472 via cartopy NorthPolarStereo) ------------------------ */
 int  st_xy2latlon(int device, int64_t n, const double *yx, double *latlon, double lat_ts, double lon0);

@@ -38,6 +38,8 @@ def __argument_parsing__():
     parser.add_argument('-p', '--plot', type=int, default=0, help='(ignored) how often we plot the positions on a map')
     parser.add_argument('--device', type=int, default=None, help='CUDA device (default: LOCAL_RANK or 0)')
     parser.add_argument('--uvstrategy', type=int, default=iUVstrategy, choices=[0, 1])
+    parser.add_argument('--rows', default='f4', choices=['f4', 'f8'],
+                        help='dtype of the trajectory rows copied off the GPU: f4 = the dtype the output files store (default), f8 = full in-memory arrays as upstream')
     args = parser.parse_args()
     print('')
     print(' *** SI3 file to get ice velocities from => ', args.fsi3)
@@ -176,7 +178,8 @@ def main():
     eng = sit.TrackEngine(xYf, xXf, xYu, xXu, xYv, xXv, tmask=imaskt, uv_strategy=args.uvstrategy, rdt=rdt,
                           rmin_conc=sit.rmin_conc, device=sit.config.device)
     eng.set_buoys(xPosC0, vJIt, z1st, zLst)
-    res = eng.track(record, Nt, kstrt=kstrt, pos0=xPosC0, posG0=xPosG0, rec_first=z1st)
+    # rows come back in the file's dtype (every trajectory variable is f4, ncio.py:153-159)
+    res = eng.track(record, Nt, kstrt=kstrt, pos0=xPosC0, posG0=xPosG0, rec_first=z1st, row_dtype=args.rows)
     eng.close()
     ds.close()
     xPosC, xPosG, xmask = res['posC'], res['posG'], res['mask']

@@ -51,6 +51,19 @@ SIGNATURES = {
     "st_step": (c_int, [vp, c_int, c_int, vp, vp, vp, vp, vp]),
     "st_step_multi": (c_int, [vp, vp, c_i64, c_int, c_int, vp, vp, vp, c_i64, vp, vp]),
     "st_track_record_host": (c_int, [vp, c_int, vp, vp, vp, vp, vp, vp, C.POINTER(c_i64)]),
+    "st_step_f4": (c_int, [vp, c_int, c_int, vp, vp, vp, vp, vp]),
+    "st_step_multi_f4": (c_int, [vp, vp, c_i64, c_int, c_int, vp, vp, vp, c_i64, vp, vp]),
+    "st_track_record_host_f4": (c_int, [vp, c_int, vp, vp, vp, vp, vp, vp, C.POINTER(c_i64)]),
+    "st_gather_create": (c_int, [vp, c_int, c_int, c_i64, c_i64, c_int, c_int, vp]),
+    "st_gather_connect_ipc": (c_int, [vp, vp]),
+    "st_gather_connect_ptrs": (c_int, [vp, C.POINTER(vp)]),
+    "st_gather_block": (c_int, [vp, C.POINTER(vp), C.POINTER(c_i64)]),
+    "st_gather_buffer": (c_int, [vp, c_int, C.POINTER(vp)]),
+    "st_step_gather": (c_int, [vp, c_int, c_int, c_int, C.c_uint64, vp, vp, vp, vp]),
+    "st_gather_wait": (c_int, [vp, C.c_uint64, vp]),
+    "st_gather_ack": (c_int, [vp, C.c_uint64, vp]),
+    "st_gather_timed_out": (c_int, [vp, C.POINTER(c_int)]),
+    "st_gather_destroy": (c_int, [vp]),
     "st_xy2latlon": (c_int, [c_int, c_i64, vp, vp, c_dbl, c_dbl]),
     "st_latlon2xy": (c_int, [c_int, c_i64, vp, vp, c_dbl, c_dbl]),
     "st_xy2latlon_dev": (c_int, [c_i64, vp, vp, c_dbl, c_dbl, vp]),
@@ -74,7 +87,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             f = getattr(L, name)
             f.restype, f.argtypes = res, args
-        if L.st_abi_version() != 1:
+        if L.st_abi_version() != 2:
             raise SitrackCudaError("libsitrack_b200.so ABI version mismatch")
         _lib = L
     return _lib

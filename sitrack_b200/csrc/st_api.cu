@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <string>
 #include <vector>
 
@@ -39,6 +40,16 @@ struct st_ctx {
     // host-API scratch outputs
     pt *o_yx = nullptr, *o_ll = nullptr; int8_t* o_mask = nullptr; unsigned long long* o_nalive = nullptr;
     long long capOut = 0;
+    // fused position all-gather over peer memory (st_gather_*)
+    struct Gather {
+        int rank = 0, world = 0, f4 = 0, nbuf = 0;
+        long long nP_total = 0, offset = 0;
+        size_t buf_bytes = 0, flags_off = 0, block_bytes = 0;
+        char* base = nullptr;                 // this rank's block: nbuf gathered arrays, then the flag page
+        char* peer[ST_MAX_PEERS + 1] = {};    // every rank's block as mapped here (peer[rank] == base)
+        bool ipc_opened[ST_MAX_PEERS + 1] = {};
+        bool connected = false;
+    } ga;
     // record slots
     std::vector<float*> d_rec, h_rec;
     cudaStream_t stream = nullptr;
@@ -251,7 +262,7 @@ int st_create(st_ctx** out, int device, int Nj, int Ni, const double* Yf, const 
 
 int st_set_kernel_variant(st_ctx* c, int variant)
 {
-    if (!c || variant < 0 || variant > 9 || variant == 2 || variant == 3 || variant == 5 || variant == 6) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 persistent tuned (default), 1 v1, 4/9 one-block-per-tile tuned, 7 persistent 128x8, 8 TMA pipelined");
+    if (!c || variant < 0 || variant > 11 || variant == 2 || variant == 3 || variant == 5 || variant == 6) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 persistent tuned (default), 1 v1, 4/9 one-block-per-tile tuned, 7 persistent 128x8, 8 TMA pipelined");
     c->variant = variant;
     return ST_OK;
 }
@@ -266,6 +277,7 @@ void st_destroy(st_ctx* c)
     cudaFree(c->o_yx); cudaFree(c->o_ll); cudaFree(c->o_mask); cudaFree(c->o_nalive);
     for (float* p : c->d_rec) cudaFree(p);
     for (float* p : c->h_rec) cudaFreeHost(p);
+    st_gather_destroy(c);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -558,20 +570,34 @@ static BuoyState state_of(st_ctx* c)
     return s;
 }
 
-int st_step(st_ctx* c, int slot, int jrec, double* out_yx, double* out_latlon, int8_t* out_mask,
-            uint64_t* n_alive, void* stream)
+static int step_impl(st_ctx* c, int slot, int jrec, void* out_yx, void* out_latlon, int8_t* out_mask,
+                     uint64_t* n_alive, int f4, void* stream)
 {
     int rc = check_slot(c, slot); if (rc) return rc;
     CU(c, cudaSetDevice(c->device));
     const size_t npt = (size_t)c->Nj * c->Ni;
     const float* r = c->d_rec[slot];
     StepOut o{(pt*)out_yx, (pt*)out_latlon, out_mask, (unsigned long long*)n_alive};
+    o.f4 = f4;
     CU(c, launch_advect_step(c->grid, r, r + npt, r + 2 * npt, state_of(c), jrec, o, c->variant, (cudaStream_t)stream));
     return ST_OK;
 }
 
-int st_step_multi(st_ctx* c, const float* rec_dev, int64_t rec_stride, int nrec, int jrec0, double* out_yx,
-                  double* out_latlon, int8_t* out_mask, int64_t out_stride, uint64_t* n_alive, void* stream)
+int st_step(st_ctx* c, int slot, int jrec, double* out_yx, double* out_latlon, int8_t* out_mask,
+            uint64_t* n_alive, void* stream)
+{
+    return step_impl(c, slot, jrec, out_yx, out_latlon, out_mask, n_alive, 0, stream);
+}
+
+int st_step_f4(st_ctx* c, int slot, int jrec, float* out_yx, float* out_latlon, int8_t* out_mask,
+               uint64_t* n_alive, void* stream)
+{
+    return step_impl(c, slot, jrec, out_yx, out_latlon, out_mask, n_alive, 1, stream);
+}
+
+static int step_multi_impl(st_ctx* c, const float* rec_dev, int64_t rec_stride, int nrec, int jrec0, void* out_yx,
+                           void* out_latlon, int8_t* out_mask, int64_t out_stride, uint64_t* n_alive, int f4,
+                           void* stream)
 {
     if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
     const long long npt = (long long)c->Nj * c->Ni;
@@ -579,12 +605,230 @@ int st_step_multi(st_ctx* c, const float* rec_dev, int64_t rec_stride, int nrec,
     if (out_stride < c->nP) return fail(c, ST_EINVAL, "st_step_multi: out_stride < nP");
     CU(c, cudaSetDevice(c->device));
     StepOut o{(pt*)out_yx, (pt*)out_latlon, out_mask, (unsigned long long*)n_alive};
+    o.f4 = f4;
     CU(c, launch_advect_multi(c->grid, rec_dev, rec_stride, nrec, state_of(c), jrec0, o, out_stride, (cudaStream_t)stream));
     return ST_OK;
 }
 
-int st_track_record_host(st_ctx* c, int jrec, const float* u, const float* v, const float* ic, double* out_yx,
-                         double* out_latlon, int8_t* out_mask, int64_t* n_alive)
+int st_step_multi(st_ctx* c, const float* rec_dev, int64_t rec_stride, int nrec, int jrec0, double* out_yx,
+                  double* out_latlon, int8_t* out_mask, int64_t out_stride, uint64_t* n_alive, void* stream)
+{
+    return step_multi_impl(c, rec_dev, rec_stride, nrec, jrec0, out_yx, out_latlon, out_mask, out_stride, n_alive, 0, stream);
+}
+
+int st_step_multi_f4(st_ctx* c, const float* rec_dev, int64_t rec_stride, int nrec, int jrec0, float* out_yx,
+                     float* out_latlon, int8_t* out_mask, int64_t out_stride, uint64_t* n_alive, void* stream)
+{
+    return step_multi_impl(c, rec_dev, rec_stride, nrec, jrec0, out_yx, out_latlon, out_mask, out_stride, n_alive, 1, stream);
+}
+
+// ---- fused position all-gather over peer memory ---------------------------------------------------
+// Block layout, identical on every rank: nbuf gathered arrays of nP_total rows (16 B f8 pairs or 8 B f4
+// pairs), then a 256-byte-aligned flag page: ready[world] u64, ack[world] u64 (at +128 B), err u32 (+256 B).
+//   ready[s] on rank r : last sequence number whose rows rank s has finished storing into r's buffers
+//   ack[s]   on rank r : last sequence number rank s has finished reading from ITS buffers, i.e. r may
+//                        overwrite the buffer that sequence used on s
+namespace {
+constexpr size_t GA_ACK_OFF = 128, GA_ERR_OFF = 256, GA_FLAG_BYTES = 512;
+struct FlagTargets { unsigned long long* p[ST_MAX_PEERS + 1]; int n; };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// one thread per flag: everything this stream did before (the step kernel's remote row stores included)
+// is ordered before the flag by the system-scope release
+__global__ void k_gather_signal(FlagTargets t, unsigned long long seq)
+{
+    const int i = threadIdx.x;
+    if (i < t.n) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(t.p[i]), "l"(seq) : "memory");
+    }
+}
+// one thread per flag spins until it reaches `target`; gives up after timeout_ns and raises *err so a
+// lost peer turns into an error code on the host instead of a hung GPU
+__global__ void k_gather_wait(const unsigned long long* flags, int n, unsigned long long target,
+                              unsigned int* err, unsigned long long timeout_ns)
+{
+    const int i = threadIdx.x;
+    if (i < n) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys(flags + i) < target) {
+            if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(err, 1u); break; }
+            __nanosleep(200);
+        }
+    }
+}
+}  // namespace
+
+int st_gather_create(st_ctx* c, int rank, int world, int64_t nP_total, int64_t offset, int f4, int nbuf,
+                     void* handle_out)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (world < 1 || world > ST_MAX_PEERS + 1 || rank < 0 || rank >= world || nbuf < 1 || nbuf > 8)
+        return fail(c, ST_EINVAL, "st_gather_create: 1 <= world <= 16, 0 <= rank < world, 1 <= nbuf <= 8");
+    if (nP_total < 0 || offset < 0 || offset + c->nP > nP_total)
+        return fail(c, ST_EINVAL, "st_gather_create: this rank's block [offset, offset+nP) must lie inside nP_total (call st_set_buoys first)");
+    CU(c, cudaSetDevice(c->device));
+    st_gather_destroy(c);
+    st_ctx::Gather& g = c->ga;
+    g.rank = rank; g.world = world; g.f4 = f4 ? 1 : 0; g.nbuf = nbuf; g.nP_total = nP_total; g.offset = offset;
+    const size_t row = g.f4 ? 8 : 16;
+    g.buf_bytes = ((size_t)nP_total * row + 255) / 256 * 256;
+    g.flags_off = g.buf_bytes * nbuf;
+    g.block_bytes = g.flags_off + GA_FLAG_BYTES;
+    CU(c, cudaMalloc(&g.base, g.block_bytes));
+    CU(c, cudaMemset(g.base + g.flags_off, 0, GA_FLAG_BYTES));
+    g.peer[rank] = g.base;
+    if (handle_out) {
+        cudaIpcMemHandle_t h;
+        CU(c, cudaIpcGetMemHandle(&h, g.base));
+        static_assert(sizeof(h) == ST_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(handle_out, &h, sizeof(h));
+    }
+    g.connected = (world == 1);
+    return ST_OK;
+}
+
+int st_gather_connect_ipc(st_ctx* c, const void* handles)
+{
+    if (!c || !c->ga.base || !handles) return fail(c, ST_ESTATE, "st_gather_connect_ipc: call st_gather_create first");
+    CU(c, cudaSetDevice(c->device));
+    st_ctx::Gather& g = c->ga;
+    for (int r = 0; r < g.world; ++r) {
+        if (r == g.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * ST_IPC_HANDLE_BYTES, sizeof(h));
+        void* p = nullptr;
+        CU(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        g.peer[r] = (char*)p; g.ipc_opened[r] = true;
+    }
+    g.connected = true;
+    return ST_OK;
+}
+
+int st_gather_connect_ptrs(st_ctx* c, void* const* blocks)
+{
+    if (!c || !c->ga.base || !blocks) return fail(c, ST_ESTATE, "st_gather_connect_ptrs: call st_gather_create first");
+    st_ctx::Gather& g = c->ga;
+    for (int r = 0; r < g.world; ++r) {
+        if (r == g.rank) continue;
+        if (!blocks[r]) return fail(c, ST_EINVAL, "st_gather_connect_ptrs: NULL block");
+        g.peer[r] = (char*)blocks[r];
+    }
+    g.connected = true;
+    return ST_OK;
+}
+
+int st_gather_block(st_ctx* c, void** block, int64_t* block_bytes)
+{
+    if (!c || !c->ga.base) return fail(c, ST_ESTATE, "st_gather_block: call st_gather_create first");
+    if (block) *block = c->ga.base;
+    if (block_bytes) *block_bytes = (int64_t)c->ga.block_bytes;
+    return ST_OK;
+}
+
+int st_gather_buffer(st_ctx* c, int buf, void** dev)
+{
+    if (!c || !c->ga.base) return fail(c, ST_ESTATE, "st_gather_buffer: call st_gather_create first");
+    if (buf < 0 || buf >= c->ga.nbuf || !dev) return fail(c, ST_EINVAL, "st_gather_buffer: bad buffer index");
+    *dev = c->ga.base + (size_t)buf * c->ga.buf_bytes;
+    return ST_OK;
+}
+
+static int gather_wait_impl(st_ctx* c, size_t off, uint64_t target, void* stream)
+{
+    st_ctx::Gather& g = c->ga;
+    char* fl = g.base + g.flags_off;
+    k_gather_wait<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)(fl + off), g.world, target,
+                                                      (unsigned int*)(fl + GA_ERR_OFF), 10ull * 1000 * 1000 * 1000);
+    CU(c, cudaGetLastError());
+    return ST_OK;
+}
+static int gather_signal_impl(st_ctx* c, size_t off, uint64_t seq, void* stream)
+{
+    st_ctx::Gather& g = c->ga;
+    FlagTargets t; t.n = g.world;
+    for (int r = 0; r < g.world; ++r)
+        t.p[r] = (unsigned long long*)(g.peer[r] + g.flags_off + off) + g.rank;
+    k_gather_signal<<<1, 32, 0, (cudaStream_t)stream>>>(t, seq);
+    CU(c, cudaGetLastError());
+    return ST_OK;
+}
+
+int st_step_gather(st_ctx* c, int slot, int jrec, int buf, uint64_t seq, void* out_latlon, int8_t* out_mask,
+                   uint64_t* n_alive, void* stream)
+{
+    int rc = check_slot(c, slot); if (rc) return rc;
+    st_ctx::Gather& g = c->ga;
+    if (!g.base || !g.connected) return fail(c, ST_ESTATE, "st_step_gather: st_gather_create / st_gather_connect_* first");
+    if (buf < 0 || buf >= g.nbuf || seq == 0) return fail(c, ST_EINVAL, "st_step_gather: bad buffer index or seq == 0");
+    if (g.offset + c->nP > g.nP_total) return fail(c, ST_ESTATE, "st_step_gather: buoy count changed since st_gather_create");
+    CU(c, cudaSetDevice(c->device));
+    // the rows written nbuf sequence numbers ago into this buffer must have been consumed everywhere
+    if (seq > (uint64_t)g.nbuf) { rc = gather_wait_impl(c, GA_ACK_OFF, seq - g.nbuf, stream); if (rc) return rc; }
+    const size_t npt = (size_t)c->Nj * c->Ni;
+    const float* r = c->d_rec[slot];
+    const size_t row = g.f4 ? 8 : 16;
+    const size_t at = (size_t)buf * g.buf_bytes + (size_t)g.offset * row;
+    StepOut o{(pt*)(g.base + at), (pt*)out_latlon, out_mask, (unsigned long long*)n_alive};
+    o.f4 = g.f4;
+    o.npeer = 0;
+    for (int k = 0; k < g.world; ++k)
+        if (k != g.rank) o.peer_yx[o.npeer++] = g.peer[k] + at;
+    CU(c, launch_advect_step(c->grid, r, r + npt, r + 2 * npt, state_of(c), jrec, o, c->variant, (cudaStream_t)stream));
+    return gather_signal_impl(c, 0, seq, stream);
+}
+
+int st_gather_wait(st_ctx* c, uint64_t seq, void* stream)
+{
+    if (!c || !c->ga.base || !c->ga.connected) return fail(c, ST_ESTATE, "st_gather_wait: no gather group");
+    CU(c, cudaSetDevice(c->device));
+    return gather_wait_impl(c, 0, seq, stream);
+}
+
+int st_gather_ack(st_ctx* c, uint64_t seq, void* stream)
+{
+    if (!c || !c->ga.base || !c->ga.connected) return fail(c, ST_ESTATE, "st_gather_ack: no gather group");
+    CU(c, cudaSetDevice(c->device));
+    return gather_signal_impl(c, GA_ACK_OFF, seq, stream);
+}
+
+int st_gather_timed_out(st_ctx* c, int* timed_out)
+{
+    if (!c || !c->ga.base || !timed_out) return fail(c, ST_ESTATE, "st_gather_timed_out: no gather group");
+    CU(c, cudaSetDevice(c->device));
+    unsigned int e = 0;
+    CU(c, cudaMemcpy(&e, c->ga.base + c->ga.flags_off + GA_ERR_OFF, sizeof(e), cudaMemcpyDeviceToHost));
+    *timed_out = (int)e;
+    return ST_OK;
+}
+
+int st_gather_destroy(st_ctx* c)
+{
+    if (!c) return ST_OK;
+    st_ctx::Gather& g = c->ga;
+    if (g.base) {
+        cudaSetDevice(c->device);
+        for (int r = 0; r < g.world; ++r)
+            if (g.ipc_opened[r] && g.peer[r]) cudaIpcCloseMemHandle(g.peer[r]);
+        cudaFree(g.base);
+    }
+    g = st_ctx::Gather{};
+    return ST_OK;
+}
+
+static int track_record_host_impl(st_ctx* c, int jrec, const float* u, const float* v, const float* ic, void* out_yx,
+                                  void* out_latlon, int8_t* out_mask, int64_t* n_alive, int f4)
 {
     if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
     if (!u || !v || !ic) return fail(c, ST_EINVAL, "st_track_record_host: u, v, ic are required");
@@ -612,10 +856,12 @@ int st_track_record_host(st_ctx* c, int jrec, const float* u, const float* v, co
     if (n_alive) CU(c, cudaMemsetAsync(c->o_nalive, 0, sizeof(unsigned long long), s));
     StepOut o{out_yx ? c->o_yx : nullptr, out_latlon ? c->o_ll : nullptr, out_mask ? c->o_mask : nullptr,
               n_alive ? c->o_nalive : nullptr};
+    o.f4 = f4;
+    const size_t rowb = f4 ? sizeof(float2) : sizeof(pt);
     CU(c, launch_advect_step(c->grid, d, d + npt, d + 2 * npt, state_of(c), jrec, o, c->variant, s));
     if (c->nP > 0) {
-        if (out_yx) CU(c, cudaMemcpyAsync(out_yx, c->o_yx, sizeof(pt) * c->nP, cudaMemcpyDeviceToHost, s));
-        if (out_latlon) CU(c, cudaMemcpyAsync(out_latlon, c->o_ll, sizeof(pt) * c->nP, cudaMemcpyDeviceToHost, s));
+        if (out_yx) CU(c, cudaMemcpyAsync(out_yx, c->o_yx, rowb * c->nP, cudaMemcpyDeviceToHost, s));
+        if (out_latlon) CU(c, cudaMemcpyAsync(out_latlon, c->o_ll, rowb * c->nP, cudaMemcpyDeviceToHost, s));
         if (out_mask) CU(c, cudaMemcpyAsync(out_mask, c->o_mask, (size_t)c->nP, cudaMemcpyDeviceToHost, s));
     }
     unsigned long long na = 0;
@@ -623,6 +869,18 @@ int st_track_record_host(st_ctx* c, int jrec, const float* u, const float* v, co
     CU(c, cudaStreamSynchronize(s));
     if (n_alive) *n_alive = (int64_t)na;
     return ST_OK;
+}
+
+int st_track_record_host(st_ctx* c, int jrec, const float* u, const float* v, const float* ic, double* out_yx,
+                         double* out_latlon, int8_t* out_mask, int64_t* n_alive)
+{
+    return track_record_host_impl(c, jrec, u, v, ic, out_yx, out_latlon, out_mask, n_alive, 0);
+}
+
+int st_track_record_host_f4(st_ctx* c, int jrec, const float* u, const float* v, const float* ic, float* out_yx,
+                            float* out_latlon, int8_t* out_mask, int64_t* n_alive)
+{
+    return track_record_host_impl(c, jrec, u, v, ic, out_yx, out_latlon, out_mask, n_alive, 1);
 }
 
 // ---- projections and batched predicates (host in/out) -------------------------------------------

@@ -31,12 +31,44 @@ struct BuoyState {
 };
 
 // One trajectory row (all nullable).
+constexpr int ST_MAX_PEERS = 15;
 struct StepOut {
     pt* yx;                     // (nP) [y,x] km     -> xPosC[jt+1]
     pt* latlon;                 // (nP) [lat,lon]    -> xPosG[jt+1]
     int8_t* mask;               // (nP)              -> xmask[jt+1,:,0]
     unsigned long long* n_alive;
+    // Rows in the output file's dtype: yx / latlon (and peer_yx) then point at (nP,2) f4 and every
+    // value is rounded once, to nearest even, exactly like the f8 -> f4 cast of ncio.py:156-159.
+    int f4;
+    // Fused position all-gather: the yx row is also stored, by the same thread in the same kernel, into
+    // npeer remote buffers (peer-mapped HBM of the other ranks over NVLink), each already offset to
+    // this rank's block of the gathered (nP_total,2) array.
+    int npeer;
+    void* peer_yx[ST_MAX_PEERS];
 };
+
+__device__ __forceinline__ void put_row_pt(void* base, long long p, pt v, int f4)
+{
+    if (f4) __stcs(reinterpret_cast<float2*>(base) + p, make_float2(__double2float_rn(v.y), __double2float_rn(v.x)));
+    else    st_stream_pt(reinterpret_cast<pt*>(base) + p, v);
+}
+// remote rows: plain (write-back) stores, the link packs them; visibility to the peer is given by the
+// release of the ready flag that follows the kernel (st_api.cu: k_gather_signal)
+__device__ __forceinline__ void put_row_yx(const StepOut& o, long long p, pt v)
+{
+    put_row_pt(o.yx, p, v, o.f4);
+    if (o.npeer) {
+        if (o.f4) {
+            const float2 w = make_float2(__double2float_rn(v.y), __double2float_rn(v.x));
+#pragma unroll 1
+            for (int k = 0; k < o.npeer; ++k) reinterpret_cast<float2*>(o.peer_yx[k])[p] = w;
+        } else {
+            const double2 w = make_double2(v.y, v.x);
+#pragma unroll 1
+            for (int k = 0; k < o.npeer; ++k) reinterpret_cast<double2*>(o.peer_yx[k])[p] = w;
+        }
+    }
+}
 
 cudaError_t launch_advect_step(const AdvectGrid& g, const float* u, const float* v, const float* ic,
                                const BuoyState& s, int jrec, const StepOut& o, int variant, cudaStream_t st);

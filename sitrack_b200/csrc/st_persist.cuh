@@ -106,12 +106,12 @@ k_advect_persist(const AdvectGrid g, const float* __restrict__ u, const float* _
             outp = P; m = 1;
         }
         if (valid) {
-            if (o.yx) st_stream_pt(o.yx + p, outp);
+            if (o.yx) put_row_yx(o, p, outp);
             if (o.mask) __stcs(o.mask + p, m);
             if (o.latlon) {
                 pt ll; ll.y = g.proj.fill_lat; ll.x = g.proj.fill_lon;            // :493 on a fill row
                 if (m) ll = inv_stere_fast(outp, g.proj, g.atab);
-                st_stream_pt(o.latlon + p, ll);
+                put_row_pt(o.latlon, p, ll, o.f4);
             }
         }
         // append this tile's crossings to the queue (deterministic order: warp, then lane)

@@ -221,12 +221,12 @@ k_advect_pipe(const AdvectGrid g, const float* __restrict__ u, const float* __re
             st_stream_pt(s.pos + p, outp);
         }
         if (valid) {
-            if (o.yx) st_stream_pt(o.yx + p, outp);
+            if (o.yx) put_row_yx(o, p, outp);
             if (o.mask) __stcs(o.mask + p, m);
             if (o.latlon) {
                 pt ll; ll.y = g.proj.fill_lat; ll.x = g.proj.fill_lon;
                 if (m) ll = inv_stere_fast(outp, g.proj, g.atab);
-                st_stream_pt(o.latlon + p, ll);
+                put_row_pt(o.latlon, p, ll, o.f4);
             }
         }
         // ---- queue the crossings of the tile ----------------------------------------------------

@@ -38,6 +38,31 @@ def _sptr(stream):
     return stream.cuda_stream
 
 
+def _rows_f4(*outs):
+    """True when the caller's row buffers are float32 (torch tensors or numpy arrays); mixing raises."""
+    kinds = {str(o.dtype).replace("torch.", "") for o in outs if o is not None}
+    if not kinds:
+        return False
+    if kinds == {"float32"}:
+        return True
+    if kinds == {"float64"}:
+        return False
+    raise TypeError("trajectory row buffers must be all float64 or all float32, got %s" % sorted(kinds))
+
+
+class _DevMem:
+    """__cuda_array_interface__ carrier so torch can view library-owned device memory."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def _tensor_from_ptr(torch, ptr, shape, dtype, itemsize, device):
+    ts = {4: "<f4", 8: "<f8"}[itemsize]
+    return torch.as_tensor(_DevMem(ptr, shape, ts), device=torch.device("cuda", device))
+
+
 class TrackEngine:
     def __init__(self, Yf, Xf, Yu=None, Xu=None, Yv=None, Xv=None, tmask=None, uv_strategy=1,
                  rdt=3600.0, rmin_conc=0.1, device=0):
@@ -182,30 +207,90 @@ class TrackEngine:
     # -- the step ----------------------------------------------------------------------
     def step(self, slot, jrec, out_yx=None, out_latlon=None, out_mask=None, n_alive=None, stream=None):
         """Enqueue one record for all buoys (async).  out_* are CUDA tensors (nP,2) f8 /
-        (nP,) i1; n_alive a CUDA int64 scalar tensor that gets incremented."""
-        check(self.L.st_step(self.h, slot, int(jrec), _dptr(out_yx), _dptr(out_latlon), _dptr(out_mask),
-                             _dptr(n_alive), _sptr(stream)), self.h)
+        (nP,) i1; n_alive a CUDA int64 scalar tensor that gets incremented.  float32 out_yx /
+        out_latlon tensors select the file-dtype rows (st_step_f4; ncio.py:153-159)."""
+        fn = self.L.st_step_f4 if _rows_f4(out_yx, out_latlon) else self.L.st_step
+        check(fn(self.h, slot, int(jrec), _dptr(out_yx), _dptr(out_latlon), _dptr(out_mask),
+                 _dptr(n_alive), _sptr(stream)), self.h)
 
     def step_multi(self, rec_stack, jrec0, out_yx=None, out_latlon=None, out_mask=None, n_alive=None,
                    stream=None):
         """rec_stack: CUDA tensor (nrec,3,Nj,Ni) f4; outputs (nrec,nP,2)/(nrec,nP); one launch."""
         nrec = rec_stack.shape[0]
         assert rec_stack.is_contiguous() and tuple(rec_stack.shape[1:]) == (3, self.Nj, self.Ni)
-        check(self.L.st_step_multi(self.h, _dptr(rec_stack), 3 * self.Nj * self.Ni, nrec, int(jrec0),
-                                   _dptr(out_yx), _dptr(out_latlon), _dptr(out_mask), self.nP,
-                                   _dptr(n_alive), _sptr(stream)), self.h)
+        fn = self.L.st_step_multi_f4 if _rows_f4(out_yx, out_latlon) else self.L.st_step_multi
+        check(fn(self.h, _dptr(rec_stack), 3 * self.Nj * self.Ni, nrec, int(jrec0),
+                 _dptr(out_yx), _dptr(out_latlon), _dptr(out_mask), self.nP,
+                 _dptr(n_alive), _sptr(stream)), self.h)
 
     def track_record_host(self, jrec, u, v, ic, out_yx=None, out_latlon=None, out_mask=None, want_alive=True):
-        """Synchronous host-buffer form of one loop iteration (H2D + step + D2H)."""
+        """Synchronous host-buffer form of one loop iteration (H2D + step + D2H).  float32 out_yx /
+        out_latlon arrays select the file-dtype rows (ncio.py:153-159)."""
         na = C.c_int64(0)
-        check(self.L.st_track_record_host(self.h, int(jrec), hptr(u), hptr(v), hptr(ic), hptr(out_yx),
-                                          hptr(out_latlon), hptr(out_mask), C.byref(na) if want_alive else None),
+        fn = self.L.st_track_record_host_f4 if _rows_f4(out_yx, out_latlon) else self.L.st_track_record_host
+        check(fn(self.h, int(jrec), hptr(u), hptr(v), hptr(ic), hptr(out_yx),
+                 hptr(out_latlon), hptr(out_mask), C.byref(na) if want_alive else None),
               self.h)
         return na.value
 
+    # -- fused all-gather of positions over peer memory (multi-GPU) ----------------------------------
+    def gather_create(self, rank, world, nP_total, offset, f4=False, nbuf=2):
+        """Allocate this rank's gathered block; returns its 64-byte CUDA IPC handle (bytes)."""
+        h = (C.c_ubyte * 64)()
+        check(self.L.st_gather_create(self.h, int(rank), int(world), int(nP_total), int(offset), int(bool(f4)),
+                                      int(nbuf), C.cast(h, C.c_void_p)), self.h)
+        self._ga = dict(rank=rank, world=world, nP_total=int(nP_total), f4=bool(f4), nbuf=int(nbuf))
+        return bytes(h)
+
+    def gather_connect_ipc(self, handles):
+        """handles: world x 64 bytes in rank order (other processes' gather_create results)."""
+        blob = b"".join(handles) if not isinstance(handles, (bytes, bytearray)) else bytes(handles)
+        assert len(blob) == 64 * self._ga["world"]
+        buf = C.create_string_buffer(blob, len(blob))
+        check(self.L.st_gather_connect_ipc(self.h, C.cast(buf, C.c_void_p)), self.h)
+
+    def gather_block(self):
+        p, n = C.c_void_p(), C.c_int64()
+        check(self.L.st_gather_block(self.h, C.byref(p), C.byref(n)), self.h)
+        return p.value, n.value
+
+    def gather_connect_ptrs(self, blocks):
+        """blocks: device pointers of every rank's block (ranks living in this process)."""
+        arr = (C.c_void_p * len(blocks))(*blocks)
+        check(self.L.st_gather_connect_ptrs(self.h, arr), self.h)
+
+    def gather_buffer(self, buf):
+        """The gathered (nP_total,2) array of buffer `buf` as a CUDA tensor view (f8 or f4)."""
+        torch = _torch()
+        p = C.c_void_p()
+        check(self.L.st_gather_buffer(self.h, int(buf), C.byref(p)), self.h)
+        g = self._ga
+        dt, isz = (torch.float32, 4) if g["f4"] else (torch.float64, 8)
+        return _tensor_from_ptr(torch, p.value, (g["nP_total"], 2), dt, isz, self.device)
+
+    def step_gather(self, slot, jrec, buf, seq, out_latlon=None, out_mask=None, n_alive=None, stream=None):
+        """st_step whose yx row lands in buffer `buf` of EVERY rank (stores over NVLink from inside the
+        step kernel); seq = 1, 2, 3, ... per record."""
+        check(self.L.st_step_gather(self.h, int(slot), int(jrec), int(buf), int(seq), _dptr(out_latlon),
+                                    _dptr(out_mask), _dptr(n_alive), _sptr(stream)), self.h)
+
+    def gather_wait(self, seq, stream=None):
+        check(self.L.st_gather_wait(self.h, int(seq), _sptr(stream)), self.h)
+
+    def gather_ack(self, seq, stream=None):
+        check(self.L.st_gather_ack(self.h, int(seq), _sptr(stream)), self.h)
+
+    def gather_timed_out(self):
+        v = C.c_int(0)
+        check(self.L.st_gather_timed_out(self.h, C.byref(v)), self.h)
+        return bool(v.value)
+
+    def gather_destroy(self):
+        check(self.L.st_gather_destroy(self.h), self.h)
+
     # -- the record loop ---------------------------------------------------------------
     def track(self, records, nrec, kstrt=0, pos0=None, posG0=None, rec_first=None, want_latlon=True,
-              sink=None, chunk=None, verbose=None):
+              sink=None, chunk=None, verbose=None, row_dtype="f8"):
         """The record loop (si3_part_tracker.py:361-496), pipelined.
 
         records: callable k -> (u, v, ic) arrays (Nj,Ni) for record index k (0-based
@@ -216,30 +301,35 @@ class TrackEngine:
         pinned host rows.  With sink=None the full (nrec+1,nP,..) series is returned
         (rows 0 from pos0/posG0); otherwise sink(jt, yx, latlon, mask) is called with
         pinned row views that are only valid during the call.
+        row_dtype "f4" moves the rows in the output file's dtype (ncio.py:153-159: 17 B per buoy
+        instead of 33 B over PCIe, values = the f8 rows cast to f4); the state stays f8 on the device.
         """
         torch = _torch()
         dev = torch.device("cuda", self.device)
         nP = self.nP
         get = _record_getter(records)
+        if row_dtype not in ("f8", "f4"):
+            raise ValueError("row_dtype must be 'f8' or 'f4'")
+        rdt = torch.float32 if row_dtype == "f4" else torch.float64
         if chunk and chunk > 1 and sink is None:
-            return self._track_chunked(get, nrec, kstrt, pos0, posG0, rec_first, want_latlon, int(chunk))
+            return self._track_chunked(get, nrec, kstrt, pos0, posG0, rec_first, want_latlon, int(chunk), rdt)
         self.record_slots(2)
         stg = [self.staging(0), self.staging(1)]
         s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
         NB = 2
-        d_yx = [torch.empty((nP, 2), dtype=torch.float64, device=dev) for _ in range(NB)]
-        d_ll = [torch.empty((nP, 2), dtype=torch.float64, device=dev) for _ in range(NB)] if want_latlon else [None] * NB
+        d_yx = [torch.empty((nP, 2), dtype=rdt, device=dev) for _ in range(NB)]
+        d_ll = [torch.empty((nP, 2), dtype=rdt, device=dev) for _ in range(NB)] if want_latlon else [None] * NB
         d_mk = [torch.empty((nP,), dtype=torch.int8, device=dev) for _ in range(NB)]
         d_na = torch.zeros((nrec,), dtype=torch.int64, device=dev)
         keep = sink is None
         if keep:
-            posC = torch.full((nrec + 1, nP, 2), FillValue, dtype=torch.float64).pin_memory()
-            posG = torch.full((nrec + 1, nP, 2), FillValue, dtype=torch.float64).pin_memory()
+            posC = torch.full((nrec + 1, nP, 2), FillValue, dtype=rdt).pin_memory()
+            posG = torch.full((nrec + 1, nP, 2), FillValue, dtype=rdt).pin_memory()
             mask = torch.zeros((nrec + 1, nP), dtype=torch.int8).pin_memory()
             rows = lambda k: (posC[k + 1], posG[k + 1] if want_latlon else None, mask[k + 1])
         else:
-            h_yx = [torch.empty((nP, 2), dtype=torch.float64).pin_memory() for _ in range(NB)]
-            h_ll = [torch.empty((nP, 2), dtype=torch.float64).pin_memory() for _ in range(NB)]
+            h_yx = [torch.empty((nP, 2), dtype=rdt).pin_memory() for _ in range(NB)]
+            h_ll = [torch.empty((nP, 2), dtype=rdt).pin_memory() for _ in range(NB)]
             h_mk = [torch.empty((nP,), dtype=torch.int8).pin_memory() for _ in range(NB)]
             rows = lambda k: (h_yx[k % NB], h_ll[k % NB] if want_latlon else None, h_mk[k % NB])
         ev_in = [None] * nrec
@@ -318,7 +408,7 @@ def _finish_rows(posC, posG, mask, pos0, posG0, rec_first, kstrt):
             posG[0, sel] = np.asarray(posG0)[sel]
 
 
-def _track_chunked(self, get, nrec, kstrt, pos0, posG0, rec_first, want_latlon, chunk):
+def _track_chunked(self, get, nrec, kstrt, pos0, posG0, rec_first, want_latlon, chunk, rdt=None):
     """Season path for small clouds: `chunk` records at a time are staged into HBM and advanced by
     ONE launch of k_advect_multi (each thread runs its buoy through the whole chunk), instead of
     one launch per record.  Host fill of chunk c+1 || H2D || compute of chunk c || D2H of its rows."""
@@ -326,14 +416,15 @@ def _track_chunked(self, get, nrec, kstrt, pos0, posG0, rec_first, want_latlon, 
     dev = torch.device("cuda", self.device)
     nP, Nj, Ni = self.nP, self.Nj, self.Ni
     s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    rdt = rdt or torch.float64
     h_rec = [torch.empty((chunk, 3, Nj, Ni), dtype=torch.float32).pin_memory() for _ in range(2)]
     d_rec = [torch.empty((chunk, 3, Nj, Ni), dtype=torch.float32, device=dev) for _ in range(2)]
-    d_yx = [torch.empty((chunk, nP, 2), dtype=torch.float64, device=dev) for _ in range(2)]
-    d_ll = [torch.empty((chunk, nP, 2), dtype=torch.float64, device=dev) for _ in range(2)] if want_latlon else [None, None]
+    d_yx = [torch.empty((chunk, nP, 2), dtype=rdt, device=dev) for _ in range(2)]
+    d_ll = [torch.empty((chunk, nP, 2), dtype=rdt, device=dev) for _ in range(2)] if want_latlon else [None, None]
     d_mk = [torch.empty((chunk, nP), dtype=torch.int8, device=dev) for _ in range(2)]
     d_na = torch.zeros((nrec,), dtype=torch.int64, device=dev)
-    posC = torch.full((nrec + 1, nP, 2), FillValue, dtype=torch.float64).pin_memory()
-    posG = torch.full((nrec + 1, nP, 2), FillValue, dtype=torch.float64).pin_memory()
+    posC = torch.full((nrec + 1, nP, 2), FillValue, dtype=rdt).pin_memory()
+    posG = torch.full((nrec + 1, nP, 2), FillValue, dtype=rdt).pin_memory()
     mask = torch.zeros((nrec + 1, nP), dtype=torch.int8).pin_memory()
     nch = (nrec + chunk - 1) // chunk
     ev_in, ev_cmp, ev_out = [None] * nch, [None] * nch, [None] * nch

@@ -129,9 +129,9 @@ def test_track_golden(torch, corc, gold_track, name, multi):
     assert np.abs(ll - want).max() < LATLON_TOL_DEG                  # also for the -9999 rows (:493)
 
 
-@pytest.mark.parametrize("variant", [1, 4, 7, 8, 9])
+@pytest.mark.parametrize("variant", [1, 4, 7, 8, 9, 10])
 @pytest.mark.parametrize("name", list(TRACK_CASES))
-def test_track_golden_other_kernels(torch, gold_track, name, variant):
+def test_track_golden_other_kernels(torch, corc, gold_track, name, variant):
     """v1 (straightforward), the other launch shapes of the tuned kernel and the persistent TMA/cp.async
     pipelined kernel reproduce the reference's golden trajectories bit for bit too."""
     T, g = gold_track
@@ -144,6 +144,8 @@ def test_track_golden_other_kernels(torch, gold_track, name, variant):
     assert np.array_equal(yx, T[name + "_posC"][1:]) and np.array_equal(mk, T[name + "_mask"][1:])
     assert np.array_equal(na, T[name + "_nalive"])
     assert np.array_equal(cells, T[name + "_jiT"]) and np.array_equal(alive, T[name + "_alive"])
+    want = corc.inv_stere(T[name + "_posC"][1:].reshape(-1, 2)).reshape(ll.shape)
+    assert np.abs(ll - want).max() < LATLON_TOL_DEG                  # every launch shape writes the same xPosG row
 
 
 def test_track_host_call_and_pipeline(torch, gold_track):
@@ -168,6 +170,82 @@ def test_track_host_call_and_pipeline(torch, gold_track):
         eng.track((T["U"], T["V"], T["IC"]), nrec, sink=lambda k, y, l, m: rows.append((k, y.copy(), m.copy())))
         assert [k for k, _, _ in rows] == list(range(nrec))
         assert all(np.array_equal(y, T["uv1_posC"][k + 1]) for k, y, _ in rows)
+
+
+def test_file_dtype_rows_are_the_f4_cast_of_the_f8_rows(torch, gold_track):
+    """st_step_f4 / st_step_multi_f4 / st_track_record_host_f4: rows in the output file's dtype
+    (ncio.py:153-159) equal numpy's f8 -> f4 cast of the golden rows bit for bit, for every kernel family,
+    and the f8 state on the device is untouched by the narrower rows."""
+    T, g = gold_track
+    nrec, nP = T["U"].shape[0], T["pos0"].shape[0]
+    want_yx, want_mk = T["uv1_posC"].astype(np.float32), T["uv1_mask"]
+    with engine_for(g) as eng:
+        eng.set_buoys(T["pos0"], T["jiT0"])
+        yx = np.empty((nP, 2), np.float32); ll = np.empty((nP, 2), np.float32); mk = np.empty(nP, np.int8)
+        ll8 = np.empty((nP, 2))
+        for k in range(nrec):
+            eng.track_record_host(k, T["U"][k], T["V"][k], T["IC"][k], yx, ll, mk)
+            assert np.array_equal(yx, want_yx[k + 1]) and np.array_equal(mk, want_mk[k + 1])
+        with pytest.raises(TypeError):
+            eng.track_record_host(0, T["U"][0], T["V"][0], T["IC"][0], yx, ll8, mk)
+        pos, cell, alive = eng.get_state()
+        assert np.array_equal(cell, T["uv1_jiT"][-1]) and np.array_equal(alive, T["uv1_alive"][-1])
+    for variant, chunk in ((0, None), (1, None), (4, None), (8, None), (0, 7)):
+        with engine_for(g) as eng:
+            eng.set_kernel_variant(variant)
+            eng.set_buoys(T["pos0"], T["jiT0"])
+            r = eng.track((T["U"], T["V"], T["IC"]), nrec, pos0=T["pos0"], posG0=T["posG0"], row_dtype="f4", chunk=chunk)
+            r8 = None
+            assert r["posC"].dtype == np.float32 and r["posG"].dtype == np.float32
+            assert np.array_equal(r["posC"], want_yx) and np.array_equal(r["mask"], want_mk)
+            eng.set_buoys(T["pos0"], T["jiT0"])
+            r8 = eng.track((T["U"], T["V"], T["IC"]), nrec, pos0=T["pos0"], posG0=T["posG0"], chunk=chunk)
+            assert np.array_equal(r["posG"][1:], r8["posG"][1:].astype(np.float32))     # lat/lon: the cast of the f8 row
+
+
+@pytest.mark.parametrize("f4", [False, True])
+def test_fused_position_allgather_two_ranks_one_device(torch, gold_track, f4):
+    """st_step_gather: two contexts on cuda:0 play two ranks (st_gather_connect_ptrs).  Each owns a shard
+    of the golden cloud and its step kernel stores its rows into BOTH gathered arrays; after every record
+    both arrays must equal the unsharded golden row -- the ready/ack flag protocol included (nbuf = 2)."""
+    from sitrack_b200 import dist as sdist
+    T, g = gold_track
+    nrec, nP = T["U"].shape[0], T["pos0"].shape[0]
+    b = sdist.shard_bounds(nP, 2, tile=64)
+    dev = torch.device("cuda", 0)
+    engs = [engine_for(g).__enter__() for _ in range(2)]
+    try:
+        for r, eng in enumerate(engs):
+            eng.set_buoys(T["pos0"][b[r]:b[r + 1]], T["jiT0"][b[r]:b[r + 1]])
+            eng.record_slots(1)
+            h = eng.gather_create(r, 2, nP, int(b[r]), f4=f4, nbuf=2)
+            assert len(h) == 64
+        blocks = [eng.gather_block()[0] for eng in engs]
+        for eng in engs:
+            eng.gather_connect_ptrs(blocks)
+        streams = [torch.cuda.Stream(dev) for _ in range(2)]
+        mks = [torch.empty((int(b[r + 1] - b[r]),), dtype=torch.int8, device=dev) for r in range(2)]
+        for k in range(nrec):
+            seq, buf = k + 1, k % 2
+            for r, eng in enumerate(engs):
+                st = eng.staging(0)
+                st[0], st[1], st[2] = T["U"][k], T["V"][k], T["IC"][k]
+                eng.submit_record(0, streams[r])
+                eng.step_gather(0, k, buf, seq, None, mks[r], None, streams[r])
+            for r, eng in enumerate(engs):
+                eng.gather_wait(seq, streams[r])
+            torch.cuda.synchronize()
+            want = T["uv1_posC"][k + 1]
+            for r, eng in enumerate(engs):
+                got = eng.gather_buffer(buf).cpu().numpy()
+                assert np.array_equal(got, want.astype(np.float32) if f4 else want), (k, r)
+                assert np.array_equal(mks[r].cpu().numpy(), T["uv1_mask"][k + 1][b[r]:b[r + 1]])
+                eng.gather_ack(seq, streams[r])
+        torch.cuda.synchronize()
+        assert not any(eng.gather_timed_out() for eng in engs)
+    finally:
+        for eng in engs:
+            eng.close()
 
 
 # ---- seeding ------------------------------------------------------------------------------------
