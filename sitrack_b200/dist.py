@@ -1,8 +1,11 @@
 """Multi-GPU plumbing: buoys shard by index (they never interact, reference
 si3_part_tracker.py:378-488), one process per GPU, the static grid and the current record
 replicated.  The only collectives are the optional per-output-record all-gather of trajectory
-rows and the all-reduce of the alive count; both go through torch.distributed (NCCL on GPUs,
-gloo in the CPU tests).
+rows and the all-reduce of the alive count.  Two forms of the all-gather:
+  * RowGatherer: torch.distributed all_gather_into_tensor (NCCL on GPUs, gloo in the CPU tests);
+  * PeerGather: fused into the step kernel -- every rank's k_advect_persist stores its new positions
+    straight into the gathered array of all ranks over NVLink peer memory (st_step_gather); here
+    torch.distributed only carries the 64-byte CUDA IPC handles once, at set-up.
 """
 import numpy as np
 
@@ -58,3 +61,45 @@ def allreduce_sum(t):
     import torch.distributed as dist
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+class PeerGather:
+    """Fused per-record all-gather of positions (include/sitrack_b200.h: st_gather_*).
+
+        pg = PeerGather(engine, n_global, offset)          # after engine.set_buoys(...)
+        for k in range(nrec):
+            pg.step(slot, jrec, out_latlon, out_mask, n_alive, stream)   # step + remote row stores
+            row = pg.wait(consumer_stream)                 # (n_global,2) tensor, valid on that stream
+            ...                                            # consume `row` on consumer_stream
+            pg.release(consumer_stream)                    # the buffer may be overwritten nbuf records later
+    """
+
+    def __init__(self, engine, n_global, offset, f4=False, nbuf=2, group=None):
+        import torch.distributed as dist
+        self.eng, self.nbuf, self.seq = engine, int(nbuf), 0
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            rank, world = 0, 1
+        handle = engine.gather_create(rank, world, n_global, offset, f4=f4, nbuf=nbuf)
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, handle, group=group)
+            engine.gather_connect_ipc(handles)
+            dist.barrier(group)                            # every rank has mapped every block
+
+    def step(self, slot, jrec, out_latlon=None, out_mask=None, n_alive=None, stream=None):
+        self.seq += 1
+        self.eng.step_gather(slot, jrec, (self.seq - 1) % self.nbuf, self.seq, out_latlon, out_mask, n_alive, stream)
+        return self.seq
+
+    def wait(self, stream=None, seq=None):
+        seq = self.seq if seq is None else seq
+        self.eng.gather_wait(seq, stream)
+        return self.eng.gather_buffer((seq - 1) % self.nbuf)
+
+    def release(self, stream=None, seq=None):
+        self.eng.gather_ack(self.seq if seq is None else seq, stream)
+
+    def close(self):
+        self.eng.gather_destroy()
