@@ -157,7 +157,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
+    from sitrack_b200.dist import bind_host_to_gpu
+    cores = bind_host_to_gpu(_physical_index(local))
+    log("[rank %d] host threads bound to %s" % (rank, "%d cores near the GPU" % len(cores) if cores else "all cores (no NVML affinity)"))
 
     K, W = args.steps, args.warmup
     wl = WORKLOADS[args.workload]
@@ -263,7 +267,7 @@ def run_ours(args):
     # roofline of the dominant kernel on THIS rank: algorithmic bytes / its mean launch duration.
     # The K launches run back to back on one stream, so the event span / K is the launch duration.
     achieved = (bsteps / K) * B_ALG / (ms / K * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_advect_step_v1<1,false>" if args.kernel == "v1" else ("k_advect_persist<1,false,64,16>" if args.kernel == "tuned" else "step variant %s" % args.kernel), "achieved": round(achieved, 1), "peak": peak,
+    roof = {"bound": "hbm", "kernel": "k_advect_step_v1<1,false>" if args.kernel == "v1" else ("k_advect_warp<1,false,0,32,32>" if args.kernel == "tuned" else "step variant %s" % args.kernel), "achieved": round(achieved, 1), "peak": peak,
             "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload),
             "peak_source": peak_src, "alg_bytes_per_buoy_step": B_ALG,
             "buoy_steps_per_launch": bsteps / K, "us_per_launch": round(ms / K * 1e3, 2)}
@@ -360,7 +364,7 @@ def run_ours(args):
             extra[tag] = {"value": bs_g / (ms_g * 1e-3), "unit": "buoy-steps/s", "steps": Ka,
                           "bytes_into_each_rank_per_step": int((offs[-1] - cnts[rank]) * (8 if f4 else 16)),
                           "timed_out": bool(bad),
-                          "what": "k_advect_persist stores every new (y,x) %s into the gathered array of all %d ranks "
+                          "what": "k_advect_warp stores every new (y,x) %s into the gathered array of all %d ranks "
                                   "itself (NVLink peer stores, ready/ack flags, no NCCL call)" % ("f4" if f4 else "f8", world)}
             barrier()
             eng.gather_destroy()
@@ -454,6 +458,17 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _physical_index(local):
+    """NVML counts physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list."""
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except (ValueError, IndexError):
+            return local
+    return local
 
 
 def nP_max(nP, dist, dev):

@@ -56,8 +56,10 @@ int  st_create(st_ctx **out, int device, int Nj, int Ni,
 void st_destroy(st_ctx *ctx);
 
 /* Step-kernel variant, all bit-identical in their results:
- *   0 (default) k_advect_persist 64x16: tuned step as persistent CTAs with a cross-tile walk queue;
- *   7 / 10 / 11 the same at 128x8 / 64x18 / 64x20;  4 / 9 k_advect_step, the tuned step with one block per tile (128x10 / 256x4);
+ *   0 (default) k_advect_warp 32x32: tuned step, persistent, every warp owns its tiles and its own
+ *     shared-memory queue of cell crossings (no CTA barrier); 2 / 5 the same at 64x16 / 128x8; 3 = 0;
+ *   6 / 7 / 10 / 11 k_advect_persist, the same step with one walk queue per CTA (64x16 / 128x8 / 64x18 / 64x20);
+ *   4 / 9 k_advect_step, the tuned step with one block per tile (128x10 / 256x4);
  *   1 k_advect_step_v1, the straightforward kernel (also SITRACK_B200_KERNEL=v1);
  *   8 k_advect_pipe, persistent CTAs with a TMA state ring and cp.async gathers.               */
 int  st_set_kernel_variant(st_ctx *ctx, int variant);

@@ -36,7 +36,7 @@ struct st_ctx {
     pt* pos = nullptr; int2* cell = nullptr; int8_t* alive = nullptr;
     int32_t *rec_first = nullptr, *rec_last = nullptr;
     bool has_window = false;
-    int variant = 0;            // 0 = tuned k_advect_step, 1 = k_advect_step_v1 (A/B reference)
+    int variant = 0;            // st_set_kernel_variant: 0 = k_advect_warp (default), 1 = k_advect_step_v1, ...
     // host-API scratch outputs
     pt *o_yx = nullptr, *o_ll = nullptr; int8_t* o_mask = nullptr; unsigned long long* o_nalive = nullptr;
     long long capOut = 0;
@@ -262,7 +262,7 @@ int st_create(st_ctx** out, int device, int Nj, int Ni, const double* Yf, const 
 
 int st_set_kernel_variant(st_ctx* c, int variant)
 {
-    if (!c || variant < 0 || variant > 11 || variant == 2 || variant == 3 || variant == 5 || variant == 6) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 persistent tuned (default), 1 v1, 4/9 one-block-per-tile tuned, 7 persistent 128x8, 8 TMA pipelined");
+    if (!c || variant < 0 || variant > 11) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 warp-private tuned (default; 2/3/5 other shapes), 1 v1, 4/9 one-block-per-tile tuned, 6/7/10/11 CTA-queue persistent, 8 TMA pipelined");
     c->variant = variant;
     return ST_OK;
 }
@@ -783,8 +783,9 @@ int st_step_gather(st_ctx* c, int slot, int jrec, int buf, uint64_t seq, void* o
     StepOut o{(pt*)(g.base + at), (pt*)out_latlon, out_mask, (unsigned long long*)n_alive};
     o.f4 = g.f4;
     o.npeer = 0;
-    for (int k = 0; k < g.world; ++k)
-        if (k != g.rank) o.peer_yx[o.npeer++] = g.peer[k] + at;
+    // each rank starts with its right-hand neighbour, so that at any moment the ranks' stores fan out
+    // over different destinations instead of all converging on rank 0 first
+    for (int k = 1; k < g.world; ++k) o.peer_yx[o.npeer++] = g.peer[(g.rank + k) % g.world] + at;
     CU(c, launch_advect_step(c->grid, r, r + npt, r + 2 * npt, state_of(c), jrec, o, c->variant, (cudaStream_t)stream));
     return gather_signal_impl(c, 0, seq, stream);
 }

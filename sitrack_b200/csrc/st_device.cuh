@@ -29,13 +29,8 @@ __device__ __forceinline__ unsigned long long l2_keep_policy()
 __device__ __forceinline__ pt ldg_pt(const pt* __restrict__ a, int idx)
 {
     pt r;
-#ifdef ST_X_L1KEEP
-    asm("ld.global.nc.L1::evict_last.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
-        : "=d"(r.y), "=d"(r.x) : "l"(a + idx), "l"(l2_keep_policy()));
-#else
     asm("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
         : "=d"(r.y), "=d"(r.x) : "l"(a + idx), "l"(l2_keep_policy()));
-#endif
     return r;
 }
 // streaming (touch-once) accesses: keep them out of the way of the resident

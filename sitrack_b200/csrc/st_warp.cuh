@@ -1,0 +1,145 @@
+// st_warp.cuh -- k_advect_warp: the tuned step with every warp on its own.
+//
+// k_advect_persist keeps one walk queue per CTA: each tile costs a __syncthreads, a shared count per warp
+// and a prefix over them (~45 warp instructions of bookkeeping per tile, 4 % of stall samples on the
+// barrier).  Here the bookkeeping goes:
+//   * a WARP owns its tiles of 32 buoys and its own shared-memory queue of crossings; appending is a
+//     ballot + popc, draining (32 entries, every lane busy) needs a __syncwarp only -- no CTA barrier, no
+//     counters; the alive count is one warp reduction and one atomic per warp at the end;
+//   * the row-store mode is a template parameter (ROWS 0: f8 rows into local HBM; 1: f4 rows and/or
+//     remote rows of the fused all-gather), so the default path carries no per-row mode branches.
+// Arithmetic, store addresses and results are those of k_advect_persist / k_advect_step_v1, bit for bit.
+#pragma once
+#include "st_kernels.h"
+
+namespace st {
+
+template <int UV, bool WIN, int ROWS, int BLK, int MINB>
+__global__ void __launch_bounds__(BLK, MINB)
+k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __restrict__ v,
+              const float* __restrict__ ic, BuoyState s, int jrec, StepOut o, int ntiles)
+{
+    constexpr int NW = BLK / 32, QCAP = 64;
+    __shared__ pt qP[NW][QCAP], qPn[NW][QCAP];
+    __shared__ int2 qC[NW][QCAP];
+    __shared__ unsigned qI[NW][QCAP];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int nwarps = (int)gridDim.x * NW;
+
+    auto load_state = [&](int tile, int8_t& al, pt& P, int2& c2) {
+        const long long p = (long long)tile * 32 + lane;
+        al = 0; P.y = ST_FILL; P.x = ST_FILL; c2 = make_int2(2, 2);
+        if (tile < ntiles && p < s.nP) {
+            al = __ldcs(s.alive + p);
+            P = ld_stream_pt(s.pos + p);
+            c2 = __ldcs(s.cell + p);
+        }
+    };
+    auto walk_pass = [&](int lo, int n) {
+        __syncwarp();                                             // queue entries of this warp visible
+        if (lane < n) {
+            const int e = lo + lane;
+            int2 cc = qC[wid][e];
+            const int j0 = cc.x, i0 = cc.y;
+            int8_t a2 = 1;
+            pt A, B;
+            { const double2 q = *reinterpret_cast<const double2*>(&qP[wid][e]); A.y = q.x; A.x = q.y; }
+            { const double2 q = *reinterpret_cast<const double2*>(&qPn[wid][e]); B.y = q.x; B.x = q.y; }
+            walk_cell(g, ic, A, B, cc.x, cc.y, a2);
+            const unsigned p = qI[wid][e];
+            if (cc.x != j0 || cc.y != i0) __stcs(s.cell + p, cc);
+            if (!a2) s.alive[p] = 0;
+        }
+        __syncwarp();                                             // slots may be overwritten again
+    };
+
+    int8_t al; pt P; int2 c2;
+    const int tile0 = (int)blockIdx.x * NW + wid;
+    load_state(tile0, al, P, c2);
+    int qn = 0, my_alive = 0;
+    for (int tile = tile0; tile < ntiles; tile += nwarps) {
+        const long long p = (long long)tile * 32 + lane;
+        const bool valid = p < s.nP;
+        // next tile's state: in flight while this tile is computed
+        int8_t nal; pt nP_; int2 nc2;
+        load_state(tile + nwarps, nal, nP_, nc2);
+
+        my_alive += (al == 1);
+        bool active = valid && al == 1;
+        bool prestart = false;
+        if (WIN && active) {
+            const int f = s.rec_first[p], l = s.rec_last[p];
+            prestart = (jrec + 1 == f);
+            active = (jrec >= f) && (jrec <= l);
+        }
+        const int2 cw = active ? c2 : make_int2(2, 2);
+        const int Ni = g.Ni;
+        const int c = cw.x * Ni + cw.y;
+        const pt bl = ldg_pt(g.F, c - Ni - 1), br = ldg_pt(g.F, c - Ni);
+        const pt ul = ldg_pt(g.F, c - 1),      ur = ldg_pt(g.F, c);
+        double zU, zV;
+        if (UV == 1) {
+            const pt v0 = ldg_pt(g.V, c - Ni), v1 = ldg_pt(g.V, c);
+            const pt u0 = ldg_pt(g.U, c - 1),  u1 = ldg_pt(g.U, c);
+            const float uL = __ldg(u + c - 1), uR = __ldg(u + c);
+            const float vB = __ldg(v + c - Ni), vT = __ldg(v + c);
+            const bool llum1 = intersect2seg(P, ur, v0, v1);      // si3_part_tracker.py:430
+            const bool llvm1 = intersect2seg(P, ur, u0, u1);      // :431
+            zU = (double)(llum1 ? uL : uR);
+            zV = (double)(llvm1 ? vB : vT);
+        } else {
+            zU = __dmul_rn(0.5, __dadd_rn((double)__ldg(u + c), (double)__ldg(u + c - 1)));
+            zV = __dmul_rn(0.5, __dadd_rn((double)__ldg(v + c), (double)__ldg(v + c - Ni)));
+        }
+        pt Pn;
+        Pn.x = __dadd_rn(P.x, div1000(__dmul_rn(zU, g.rdt)));      // :452-458
+        Pn.y = __dadd_rn(P.y, div1000(__dmul_rn(zV, g.rdt)));
+        const bool in = inside_quad2(Pn.y, Pn.x, bl, br, ur, ul, active);
+        const bool cross = active && !in;
+        pt outp = {ST_FILL, ST_FILL};
+        int8_t m = 0;
+        if (active) {
+            outp = Pn; m = 1;
+            st_stream_pt(s.pos + p, outp);
+        } else if (WIN && prestart) {
+            outp = P; m = 1;
+        }
+        if (valid) {
+            if (ROWS == 0) {
+                if (o.yx) st_stream_pt(o.yx + p, outp);
+            } else {
+                if (o.yx) put_row_yx(o, p, outp);
+            }
+            if (o.mask) __stcs(o.mask + p, m);
+            if (o.latlon) {
+                pt ll; ll.y = g.proj.fill_lat; ll.x = g.proj.fill_lon;            // :493 on a fill row
+                if (m) ll = inv_stere_fast(outp, g.proj, g.atab);
+                if (ROWS == 0) st_stream_pt(o.latlon + p, ll);
+                else           put_row_pt(o.latlon, p, ll, o.f4);
+            }
+        }
+        // append this tile's crossings to the warp's queue (lane order)
+        const unsigned bal = __ballot_sync(0xffffffffu, cross);
+        if (cross) {
+            const int e = qn + __popc(bal & lt);
+            *reinterpret_cast<double2*>(&qP[wid][e]) = make_double2(P.y, P.x);
+            *reinterpret_cast<double2*>(&qPn[wid][e]) = make_double2(outp.y, outp.x);
+            qC[wid][e] = c2; qI[wid][e] = (unsigned)p;
+        }
+        qn += __popc(bal);
+        if (qn >= 32) {                                            // warp-uniform
+            qn -= 32;
+            walk_pass(qn, 32);
+        }
+        al = nal; P = nP_; c2 = nc2;
+    }
+    walk_pass(0, qn);                                             // flush (qn < 32)
+    if (o.n_alive) {
+        const int wsum = __reduce_add_sync(0xffffffffu, my_alive);
+        if (lane == 0 && wsum) atomicAdd(o.n_alive, (unsigned long long)wsum);
+    }
+}
+
+}  // namespace st

@@ -103,3 +103,23 @@ class PeerGather:
 
     def close(self):
         self.eng.gather_destroy()
+
+
+def bind_host_to_gpu(device):
+    """Pin this process to the CPU cores next to `device` (NVML's cpu affinity of the GPU), so that the
+    pinned staging buffers it allocates afterwards sit on the GPU's own NUMA node and its PCIe copies do
+    not cross the socket interconnect.  Returns the core list, or None when NVML / the call is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cores = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:
+        return None
+    return None

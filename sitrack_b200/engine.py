@@ -104,7 +104,8 @@ class TrackEngine:
         self.close()
 
     def set_kernel_variant(self, variant):
-        """0 = tuned k_advect_step (default), 1 = k_advect_step_v1 (A/B reference)."""
+        """0 = k_advect_warp (default), 1 = k_advect_step_v1 (straightforward A/B reference); the other
+        launch shapes and kernel families are listed in include/sitrack_b200.h."""
         check(self.L.st_set_kernel_variant(self.h, int(variant)), self.h)
 
     # -- seeding -----------------------------------------------------------------------
