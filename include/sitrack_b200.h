@@ -141,6 +141,24 @@ int  st_step_multi(st_ctx *ctx, const float *rec_dev, int64_t rec_stride, int nr
 int  st_track_record_host(st_ctx *ctx, int jrec, const float *u, const float *v, const float *ic,
                           double *out_yx, double *out_latlon, int8_t *out_mask, int64_t *n_alive);
 
+/* ---- optional physics beyond the reference (default off) ----------------------------------
+ * The reference takes ONE Euler step per record from a face velocity picked by two segment
+ * tests and follows a buoy over at most ONE cell boundary (si3_part_tracker.py:423-484).
+ * st_step_ext is st_step with the choice left to the caller:
+ *   scheme   1 Euler, 2 midpoint Runge-Kutta, 4 classical Runge-Kutta (the record is frozen
+ *            during the step: stages differ in space only);
+ *   interp   0 the reference's pick (iUVstrategy of st_create), 1 C-grid linear (u between the
+ *            west/east U-points of the host cell, v between its south/north V-points);
+ *   max_hops cell boundaries a step or a stage may cross (>= 1); every cell entered must pass
+ *            Survive (tracking.py:62-93).
+ * State, records, kill rules, outputs and call protocol are those of st_step.  Results are NOT
+ * comparable with the reference bit for bit, not even for (1, 0, 1): the Euler update is h*u
+ * with h = rdt/1000 and the cell search is an orientation walk.  Validated against closed
+ * forms in tests/test_ext_physics.py.                                                      */
+int  st_step_ext(st_ctx *ctx, int slot, int jrec, int scheme, int interp, int max_hops,
+                 double *out_yx_dev, double *out_latlon_dev, int8_t *out_mask_dev,
+                 uint64_t *n_alive_dev, void *stream);
+
 /* ---- rows in the output file's dtype ----------------------------------------------------
  * The reference keeps xPosC/xPosG as f8 in memory and casts to f4 when it writes the file
  * (sitrack/ncio.py:153-159: every trajectory variable is created 'f4').  These variants

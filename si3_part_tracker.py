@@ -38,6 +38,11 @@ def __argument_parsing__():
     parser.add_argument('-p', '--plot', type=int, default=0, help='(ignored) how often we plot the positions on a map')
     parser.add_argument('--device', type=int, default=None, help='CUDA device (default: LOCAL_RANK or 0)')
     parser.add_argument('--uvstrategy', type=int, default=iUVstrategy, choices=[0, 1])
+    parser.add_argument('--scheme', default='euler', choices=['euler', 'rk2', 'rk4'],
+                        help='time stepping: euler = upstream behaviour (default); rk2/rk4 = optional physics (st_step_ext)')
+    parser.add_argument('--interp', default='pick', choices=['pick', 'linear'],
+                        help='velocity at the buoy: pick = upstream face pick (default); linear = C-grid linear (st_step_ext)')
+    parser.add_argument('--hops', type=int, default=1, help='cell boundaries a buoy may cross per record (upstream: 1)')
     parser.add_argument('--rows', default='f4', choices=['f4', 'f8'],
                         help='dtype of the trajectory rows copied off the GPU: f4 = the dtype the output files store (default), f8 = full in-memory arrays as upstream')
     args = parser.parse_args()
@@ -179,7 +184,12 @@ def main():
                           rmin_conc=sit.rmin_conc, device=sit.config.device)
     eng.set_buoys(xPosC0, vJIt, z1st, zLst)
     # rows come back in the file's dtype (every trajectory variable is f4, ncio.py:153-159)
-    res = eng.track(record, Nt, kstrt=kstrt, pos0=xPosC0, posG0=xPosG0, rec_first=z1st, row_dtype=args.rows)
+    physics = None
+    if args.scheme != 'euler' or args.interp != 'pick' or args.hops != 1:
+        physics = dict(scheme={'euler': 1, 'rk2': 2, 'rk4': 4}[args.scheme], interp=int(args.interp == 'linear'), max_hops=args.hops)
+        print(' *** NOTE: optional physics beyond upstream sitrack is ON:', physics)
+    res = eng.track(record, Nt, kstrt=kstrt, pos0=xPosC0, posG0=xPosG0, rec_first=z1st,
+                    row_dtype='f8' if physics else args.rows, physics=physics)
     eng.close()
     ds.close()
     xPosC, xPosG, xmask = res['posC'], res['posG'], res['mask']

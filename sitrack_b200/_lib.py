@@ -51,6 +51,7 @@ SIGNATURES = {
     "st_step": (c_int, [vp, c_int, c_int, vp, vp, vp, vp, vp]),
     "st_step_multi": (c_int, [vp, vp, c_i64, c_int, c_int, vp, vp, vp, c_i64, vp, vp]),
     "st_track_record_host": (c_int, [vp, c_int, vp, vp, vp, vp, vp, vp, C.POINTER(c_i64)]),
+    "st_step_ext": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp]),
     "st_step_f4": (c_int, [vp, c_int, c_int, vp, vp, vp, vp, vp]),
     "st_step_multi_f4": (c_int, [vp, vp, c_i64, c_int, c_int, vp, vp, vp, c_i64, vp, vp]),
     "st_track_record_host_f4": (c_int, [vp, c_int, vp, vp, vp, vp, vp, vp, C.POINTER(c_i64)]),

@@ -10,8 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libsitrack_b200.so")
-SOURCES = ["st_api.cu", "st_advect.cu", "st_locate.cu", "st_geom.cu"]
-HEADERS = ["st_device.cuh", "st_kernels.h", os.path.join("..", "..", "include", "sitrack_b200.h")]
+SOURCES = ["st_api.cu", "st_advect.cu", "st_locate.cu", "st_geom.cu", "st_ext.cu"]
+HEADERS = ["st_device.cuh", "st_kernels.h", "st_persist.cuh", "st_pipe.cuh", "st_warp.cuh", os.path.join("..", "..", "include", "sitrack_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

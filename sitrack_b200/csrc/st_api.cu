@@ -595,6 +595,23 @@ int st_step_f4(st_ctx* c, int slot, int jrec, float* out_yx, float* out_latlon, 
     return step_impl(c, slot, jrec, out_yx, out_latlon, out_mask, n_alive, 1, stream);
 }
 
+int st_step_ext(st_ctx* c, int slot, int jrec, int scheme, int interp, int max_hops, double* out_yx,
+                double* out_latlon, int8_t* out_mask, uint64_t* n_alive, void* stream)
+{
+    int rc = check_slot(c, slot); if (rc) return rc;
+    if ((scheme != 1 && scheme != 2 && scheme != 4) || (interp != 0 && interp != 1) || max_hops < 1 || max_hops > 64)
+        return fail(c, ST_EINVAL, "st_step_ext: scheme 1|2|4 (Euler, midpoint RK2, RK4), interp 0|1 (face pick, C-grid linear), 1 <= max_hops <= 64");
+    if (interp == 1 && (!c->grid.U || !c->grid.V))
+        return fail(c, ST_ESTATE, "st_step_ext: C-grid linear interpolation needs the U- and V-point coordinates (st_create with Yu,Xu,Yv,Xv)");
+    CU(c, cudaSetDevice(c->device));
+    const size_t npt = (size_t)c->Nj * c->Ni;
+    const float* r = c->d_rec[slot];
+    StepOut o{(pt*)out_yx, (pt*)out_latlon, out_mask, (unsigned long long*)n_alive};
+    CU(c, launch_advect_ext(c->grid, r, r + npt, r + 2 * npt, state_of(c), jrec, o, scheme, interp, max_hops,
+                            (cudaStream_t)stream));
+    return ST_OK;
+}
+
 static int step_multi_impl(st_ctx* c, const float* rec_dev, int64_t rec_stride, int nrec, int jrec0, void* out_yx,
                            void* out_latlon, int8_t* out_mask, int64_t out_stride, uint64_t* n_alive, int f4,
                            void* stream)

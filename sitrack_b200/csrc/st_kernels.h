@@ -72,6 +72,9 @@ __device__ __forceinline__ void put_row_yx(const StepOut& o, long long p, pt v)
 
 cudaError_t launch_advect_step(const AdvectGrid& g, const float* u, const float* v, const float* ic,
                                const BuoyState& s, int jrec, const StepOut& o, int variant, cudaStream_t st);
+cudaError_t launch_advect_ext(const AdvectGrid& g, const float* u, const float* v, const float* ic,
+                              const BuoyState& s, int jrec, const StepOut& o, int scheme, int interp, int max_hops,
+                              cudaStream_t st);
 cudaError_t launch_divcore(const double* a, const double* b, double* q_fast, double* q_div, long long n, cudaStream_t st);
 cudaError_t launch_div1000(const double* a, double* q_fast, double* q_div, long long n, cudaStream_t st);
 cudaError_t launch_advect_multi(const AdvectGrid& g, const float* rec0, long long rec_stride, int nrec,

@@ -214,6 +214,13 @@ class TrackEngine:
         check(fn(self.h, slot, int(jrec), _dptr(out_yx), _dptr(out_latlon), _dptr(out_mask),
                  _dptr(n_alive), _sptr(stream)), self.h)
 
+    def step_ext(self, slot, jrec, scheme=1, interp=0, max_hops=1, out_yx=None, out_latlon=None, out_mask=None,
+                 n_alive=None, stream=None):
+        """st_step with optional physics beyond the reference: scheme 1|2|4 (Euler, midpoint RK2, RK4),
+        interp 0|1 (the reference's face pick, C-grid linear), max_hops cell boundaries per step."""
+        check(self.L.st_step_ext(self.h, slot, int(jrec), int(scheme), int(interp), int(max_hops), _dptr(out_yx),
+                                 _dptr(out_latlon), _dptr(out_mask), _dptr(n_alive), _sptr(stream)), self.h)
+
     def step_multi(self, rec_stack, jrec0, out_yx=None, out_latlon=None, out_mask=None, n_alive=None,
                    stream=None):
         """rec_stack: CUDA tensor (nrec,3,Nj,Ni) f4; outputs (nrec,nP,2)/(nrec,nP); one launch."""
@@ -291,7 +298,7 @@ class TrackEngine:
 
     # -- the record loop ---------------------------------------------------------------
     def track(self, records, nrec, kstrt=0, pos0=None, posG0=None, rec_first=None, want_latlon=True,
-              sink=None, chunk=None, verbose=None, row_dtype="f8"):
+              sink=None, chunk=None, verbose=None, row_dtype="f8", physics=None):
         """The record loop (si3_part_tracker.py:361-496), pipelined.
 
         records: callable k -> (u, v, ic) arrays (Nj,Ni) for record index k (0-based
@@ -302,6 +309,7 @@ class TrackEngine:
         pinned host rows.  With sink=None the full (nrec+1,nP,..) series is returned
         (rows 0 from pos0/posG0); otherwise sink(jt, yx, latlon, mask) is called with
         pinned row views that are only valid during the call.
+        physics = dict(scheme=, interp=, max_hops=) switches every record to st_step_ext (f8 rows only).
         row_dtype "f4" moves the rows in the output file's dtype (ncio.py:153-159: 17 B per buoy
         instead of 33 B over PCIe, values = the f8 rows cast to f4); the state stays f8 on the device.
         """
@@ -312,6 +320,10 @@ class TrackEngine:
         if row_dtype not in ("f8", "f4"):
             raise ValueError("row_dtype must be 'f8' or 'f4'")
         rdt = torch.float32 if row_dtype == "f4" else torch.float64
+        if physics:
+            if row_dtype != "f8":
+                raise ValueError("physics modes write f8 rows")
+            chunk = None
         if chunk and chunk > 1 and sink is None:
             return self._track_chunked(get, nrec, kstrt, pos0, posG0, rec_first, want_latlon, int(chunk), rdt)
         self.record_slots(2)
@@ -356,7 +368,11 @@ class TrackEngine:
             s_cmp.wait_event(ev_in[k])
             if k >= NB:
                 s_cmp.wait_event(ev_out[k - NB])           # device out buffer b drained
-            self.step(b, k + kstrt, d_yx[b], d_ll[b], d_mk[b], d_na[k:k + 1], s_cmp)
+            if physics:
+                self.step_ext(b, k + kstrt, physics.get("scheme", 1), physics.get("interp", 0),
+                              physics.get("max_hops", 1), d_yx[b], d_ll[b], d_mk[b], d_na[k:k + 1], s_cmp)
+            else:
+                self.step(b, k + kstrt, d_yx[b], d_ll[b], d_mk[b], d_na[k:k + 1], s_cmp)
             ev_step[k] = torch.cuda.Event(); ev_step[k].record(s_cmp)
             s_out.wait_event(ev_step[k])
             if not keep and k >= NB:

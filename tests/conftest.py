@@ -42,6 +42,19 @@ def corc():
     return m
 
 
+@pytest.fixture(scope="session")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="session")
+def sit():
+    import sitrack_b200
+    return sitrack_b200
+
+
 def engine_for(g, **kw):
     import sitrack_b200 as sit
     return sit.TrackEngine(g["Yf"], g["Xf"], g["Yu"], g["Xu"], g["Yv"], g["Xv"], tmask=g["tmask"], **kw)

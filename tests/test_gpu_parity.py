@@ -15,19 +15,6 @@ pytestmark = pytest.mark.gpu
 LATLON_TOL_DEG = 1e-9
 
 
-@pytest.fixture(scope="module")
-def torch():
-    import torch
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
-    return torch
-
-
-@pytest.fixture(scope="module")
-def sit():
-    import sitrack_b200
-    return sitrack_b200
-
-
 # ---- scalar / batched predicates against the reference's golden answers -------------------
 
 def test_inside_quad_golden(sit, gold_pred):
