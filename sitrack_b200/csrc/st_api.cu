@@ -26,6 +26,7 @@ struct st_ctx {
     // owned device memory
     pt *F = nullptr, *U = nullptr, *V = nullptr;
     int8_t* tmask = nullptr;
+    int8_t* cellbits = nullptr;
     double *latT = nullptr, *lonT = nullptr, *resKM = nullptr;
     int *bin_start = nullptr, *bin_pts = nullptr;
     AngEntry* atab = nullptr;
@@ -136,6 +137,17 @@ static ProjConst make_proj(double lat_ts, double lon0)
     p.lon0_rad = lon0 * 0.017453292519943295;
     p.fill_lat = p.fill_lon = 0.0;
     fit_lat_poly(e, p.lat_poly);
+    const double R2D = 57.29577951308232, PI = 3.141592653589793;
+    for (int k = 0; k < 12; ++k) p.lat_poly_deg[k] = p.lat_poly[k] * R2D;
+    p.w_scale = 8.0 * p.k_t * p.k_t;
+    // octant tables of inv_stere_fast (st_device.cuh: folded_angle): angle = sign * (off + sg * theta)
+    const double off4[4] = {0.0, PI / 2, PI, PI / 2}, sg4[4] = {1.0, -1.0, -1.0, 1.0};
+    for (int o = 0; o < 8; ++o) {
+        const double sgn = (o & 4) ? -1.0 : 1.0;
+        p.oct_off[o] = (sgn * off4[o & 3]) * R2D + lon0;
+        p.oct_sg[o] = sgn * sg4[o & 3] * R2D;
+    }
+    p.wrap_up = lon0 > 0.0;
     return p;
 }
 static ProjFwdConst make_proj_fwd(double lat_ts, double lon0)
@@ -254,7 +266,13 @@ int st_create(st_ctx** out, int device, int Nj, int Ni, const double* Yf, const 
     e = make_angle_table(&c->atab);
     c->grid.atab = c->atab;
     if (e == cudaSuccess) e = refresh_fill(c);
-    if (e != cudaSuccess) { rc = cuda_fail(nullptr, e, "st_create(projection tables)"); st_destroy(c); return rc; }
+    if (e == cudaSuccess && uv_strategy == 1) {
+        e = cudaMalloc(&c->cellbits, n);
+        if (e == cudaSuccess) e = launch_cell_bits(c->grid, c->cellbits, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        c->grid.cellbits = c->cellbits;
+    }
+    if (e != cudaSuccess) { rc = cuda_fail(nullptr, e, "st_create(projection tables, cell bits)"); st_destroy(c); return rc; }
     { const char* ev = getenv("SITRACK_B200_KERNEL"); if (ev && ev[0] == 'v' && ev[1] == '1') c->variant = 1; }
     *out = c;
     return ST_OK;
@@ -271,7 +289,7 @@ void st_destroy(st_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->F); cudaFree(c->U); cudaFree(c->V); cudaFree(c->tmask); cudaFree(c->atab);
+    cudaFree(c->F); cudaFree(c->U); cudaFree(c->V); cudaFree(c->tmask); cudaFree(c->atab); cudaFree(c->cellbits);
     cudaFree(c->latT); cudaFree(c->lonT); cudaFree(c->resKM); cudaFree(c->bin_start); cudaFree(c->bin_pts);
     cudaFree(c->pos); cudaFree(c->cell); cudaFree(c->alive); cudaFree(c->rec_first); cudaFree(c->rec_last);
     cudaFree(c->o_yx); cudaFree(c->o_ll); cudaFree(c->o_mask); cudaFree(c->o_nalive);

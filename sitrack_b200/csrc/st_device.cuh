@@ -60,6 +60,14 @@ __device__ __forceinline__ bool intersect2seg(pt A, pt B, pt C, pt D)
     return (ccw(A, C, D) != ccw(B, C, D)) & (ccw(A, B, C) != ccw(A, B, D));
 }
 
+// The same test when ccw(B,C,D) is already known.  In the U/V pick (si3_part_tracker.py:430-431) B, C, D
+// are the cell's NE corner and two of its face points: that orientation is a property of the cell, computed
+// once per grid by k_cell_bits with this very ccw() -- same operations, same rounding, same truth value.
+__device__ __forceinline__ bool intersect2seg_pre(pt A, pt B, pt C, pt D, bool ccw_bcd)
+{
+    return (ccw(A, C, D) != ccw_bcd) & (ccw(A, B, C) != ccw(A, B, D));
+}
+
 // ---- locate.py:66-74  one edge (p1->p2) of the ray-casting parity test -------
 __device__ __forceinline__ bool edge_toggles(double y, double x, pt p1, pt p2)
 {
@@ -136,6 +144,12 @@ struct ProjConst {
     double lon0_rad;   // central longitude
     double fill_lat, fill_lon;   // inv_stere of (-9999,-9999) km: what rows of idle buoys hold (:493)
     double lat_poly[12];         // phi = pi/2 + t * sum_k lat_poly[k] (8 t^2 - 1)^k for t <= 1/2
+    // inv_stere_fast works in degrees from the start:
+    double w_scale;              // 8 k_t^2: w = 8 t^2 - 1 = r^2 w_scale - 1
+    double lat_poly_deg[12];     // lat_poly in degrees: lat = 90 + t * sum_k lat_poly_deg[k] w^k
+    double oct_off[8], oct_sg[8];   // lon = oct_off[o] + oct_sg[o] * theta, o = swap | (cos<0)<<1 | (sin<0)<<2,
+                                    // theta in [0, pi/4] the octant-folded angle; central longitude included
+    int wrap_up;                 // lon0 > 0: only lon > 180 can occur; else only lon < -180
 };
 
 __device__ __forceinline__ pt inv_stere(pt yx, const ProjConst& pc)
@@ -182,42 +196,51 @@ __device__ __forceinline__ double rsqrt_nr(double x)
     const double e = fma(-(x * y), y, 1.0);
     return fma(0.5 * y, e, y);
 }
-__device__ __forceinline__ double angle_of_unit(double s, double c, const AngEntry* __restrict__ tab)
+// octant-folded angle theta in [0, pi/4] of the direction (s, c) (any common positive scale) and its
+// octant o = swap | (c<0)<<1 | (s<0)<<2: the direction's angle from the +c axis towards +s is
+//   swap=0,c>=0: +-theta   swap=1,c>=0: +-(pi/2 - theta)   swap=0,c<0: +-(pi - theta)   swap=1,c<0: +-(pi/2 + theta)
+// with the sign of s.
+__device__ __forceinline__ double folded_angle(double s, double c, const AngEntry* __restrict__ tab, int& oct)
 {
-    const double HALFPI = 1.5707963267948966, PI = 3.141592653589793;
-    const double a = fabs(s), b = fabs(c);
-    const bool swp = a > b;
-    const double m = swp ? b : a, M = swp ? a : b;
-    int j = __double2int_rn(m * 64.0);
+    const bool swp = fabs(s) > fabs(c);
+    const double ms = swp ? c : s, Ms = swp ? s : c;           // signed; magnitudes taken at the uses
+    int j = __double2int_rn(fabs(ms) * 64.0);
     j = min(max(j, 0), 46);
     const double2 e0 = __ldg(reinterpret_cast<const double2*>(tab + j));          // alpha, cos
     const double sa = __ldg(reinterpret_cast<const double*>(tab + j) + 2);         // sin
-    const double sd = fma(m, e0.y, -(M * sa));
+    const double sd = fma(fabs(ms), e0.y, -(fabs(Ms) * sa));
     const double z = sd * sd;
     const double d = fma(sd * z, fma(z, fma(z, 15. / 336., 3. / 40.), 1. / 6.), sd);
-    double th = e0.x + d;
-    if (swp) th = HALFPI - th;
-    if (c < 0.0) th = PI - th;
+    oct = (int)swp | ((int)(c < 0.0) << 1) | ((__double2hiint(s) >> 31) & 1) << 2;
+    return e0.x + d;
+}
+__device__ __forceinline__ double angle_of_unit(double s, double c, const AngEntry* __restrict__ tab)
+{
+    const double HALFPI = 1.5707963267948966, PI = 3.141592653589793;
+    int oct;
+    double th = folded_angle(s, c, tab, oct);
+    if (oct & 1) th = HALFPI - th;
+    if (oct & 2) th = PI - th;
     return copysign(th, s);
 }
 
 __device__ __forceinline__ pt inv_stere_fast(pt yx, const ProjConst& pc, const AngEntry* __restrict__ tab)
 {
-    const double HALFPI = 1.5707963267948966, PI = 3.141592653589793, R2D = 57.29577951308232;
+    const double R2D = 57.29577951308232;
     const double r2 = fma(yx.x, yx.x, yx.y * yx.y);
     const double rinv = (r2 > 0.0) ? rsqrt_nr(r2) : 0.0;          // pole: lam = 0 like PROJ
     const double t = (r2 * rinv) * pc.k_t;
-    const double t2 = t * t;
-    double phi;
-    if (t2 <= 0.25) {
+    const double w = fma(r2, pc.w_scale, -1.0);                    // 8 t^2 - 1
+    pt r;
+    if (w <= 1.0) {
         // latitudes above ~37N: phi - pi/2 is odd in t, phi = pi/2 + t Q(8 t^2 - 1) with Q a degree-11
         // polynomial fitted at st_create for the ellipsoid (|error| < 1e-14 rad, see make_proj)
-        const double w = fma(8.0, t2, -1.0);
-        double q = pc.lat_poly[11];
+        double q = pc.lat_poly_deg[11];
 #pragma unroll
-        for (int k = 10; k >= 0; --k) q = fma(q, w, pc.lat_poly[k]);
-        phi = fma(t, q, HALFPI);
+        for (int k = 10; k >= 0; --k) q = fma(q, w, pc.lat_poly_deg[k]);
+        r.y = fma(t, q, 90.0);
     } else {
+        const double t2 = t * t;
         const double inv = rcp_nr(1.0 + t2);
         const double s = (1.0 - t2) * inv;              // sin(chi)
         const double c = (t + t) * inv;                 // cos(chi)
@@ -227,12 +250,15 @@ __device__ __forceinline__ pt inv_stere_fast(pt yx, const ProjConst& pc, const A
         double b2 = 0.0, b1 = pc.c[4];                  // c[5] = 6e-16 rad is dropped
 #pragma unroll
         for (int k = 3; k >= 0; --k) { const double b0 = fma(c2x2, b1, pc.c[k] - b2); b2 = b1; b1 = b0; }
-        phi = fma(b1, s2, chi);
+        r.y = fma(b1, s2, chi) * R2D;
     }
-    double lam = angle_of_unit(yx.x * rinv, -(yx.y * rinv), tab) + pc.lon0_rad;
-    if (lam > PI) lam -= 2.0 * PI;
-    if (lam < -PI) lam += 2.0 * PI;
-    pt r; r.y = phi * R2D; r.x = lam * R2D; return r;
+    int oct;
+    const double th = folded_angle(yx.x * rinv, -(yx.y * rinv), tab, oct);
+    double lon = fma(th, pc.oct_sg[oct], pc.oct_off[oct]);
+    if (pc.wrap_up) { if (lon > 180.0) lon -= 360.0; }
+    else            { if (lon < -180.0) lon += 360.0; }
+    r.x = lon;
+    return r;
 }
 
 // x / 1000 correctly rounded without the division sequence: q = RN(a r), r = RN(1/1000),

@@ -84,8 +84,9 @@ k_advect_persist(const AdvectGrid g, const float* __restrict__ u, const float* _
             const pt u0 = ldg_pt(g.U, c - 1),  u1 = ldg_pt(g.U, c);
             const float uL = __ldg(u + c - 1), uR = __ldg(u + c);
             const float vB = __ldg(v + c - Ni), vT = __ldg(v + c);
-            const bool llum1 = intersect2seg(P, ur, v0, v1);      // si3_part_tracker.py:430
-            const bool llvm1 = intersect2seg(P, ur, u0, u1);      // :431
+            const int cb = __ldg(g.cellbits + c);                 // orientation of (ur,v0,v1) and (ur,u0,u1)
+            const bool llum1 = intersect2seg_pre(P, ur, v0, v1, cb & 1);      // si3_part_tracker.py:430
+            const bool llvm1 = intersect2seg_pre(P, ur, u0, u1, cb & 2);      // :431
             zU = (double)(llum1 ? uL : uR);
             zV = (double)(llvm1 ? vB : vT);
         } else {
