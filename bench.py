@@ -41,6 +41,17 @@ WORKLOADS = {
 }
 
 
+# The contract is ONE JSON line on stdout.  Libraries loaded later write there too (NCCL prints its
+# version banner on fd 1 whatever NCCL_DEBUG_FILE says), so the real stdout is kept aside for the result
+# and fd 1 is pointed at stderr for everything else.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_RESULT_FD, (json.dumps(obj) + "\n").encode())
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -454,7 +465,7 @@ def run_ours(args):
                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
                "clocks": clocks, "seed_locate": {"buoys_per_s": SC_t.shape[0] / (seed_ms * 1e-3), "ms": round(seed_ms, 3)}}
         out.update(extra)
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -610,7 +621,7 @@ def run_reference(args):
            "cpu_baseline": {"value": value, "unit": "buoy-steps/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "buoy-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def _guess_cell(g, p):
