@@ -266,11 +266,18 @@ int st_create(st_ctx** out, int device, int Nj, int Ni, const double* Yf, const 
     e = make_angle_table(&c->atab);
     c->grid.atab = c->atab;
     if (e == cudaSuccess) e = refresh_fill(c);
-    if (e == cudaSuccess && uv_strategy == 1) {
+    if (e == cudaSuccess) {
+        int* d_bad = nullptr; int bad = 0;
         e = cudaMalloc(&c->cellbits, n);
-        if (e == cudaSuccess) e = launch_cell_bits(c->grid, c->cellbits, c->stream);
+        if (e == cudaSuccess) e = cudaMalloc(&d_bad, sizeof(int));
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream);
+        if (e == cudaSuccess) e = launch_cell_bits(c->grid, c->cellbits, d_bad, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(d_bad);
         c->grid.cellbits = c->cellbits;
+        // the orientation filter's error bound assumes km coordinates within 2^17 (inside_margin)
+        c->grid.filter_ok = (bad == 0) && !getenv("SITRACK_B200_NO_FILTER");
     }
     if (e != cudaSuccess) { rc = cuda_fail(nullptr, e, "st_create(projection tables, cell bits)"); st_destroy(c); return rc; }
     { const char* ev = getenv("SITRACK_B200_KERNEL"); if (ev && ev[0] == 'v' && ev[1] == '1') c->variant = 1; }

@@ -17,7 +17,9 @@ struct AdvectGrid {
     const pt* V;                // V-points (north faces)
     const int8_t* tmask;        // (Nj*Ni)
     const int8_t* cellbits;     // (Nj*Ni) per host cell: bit 0 = ccw(F[c], V[c-Ni], V[c]), bit 1 = ccw(F[c], U[c-1], U[c])
-                                //  -- the buoy-independent orientation of the two U/V-pick segment tests (k_cell_bits)
+                                //  -- the buoy-independent orientation of the two U/V-pick segment tests (k_cell_bits);
+                                //  bit 2 = the cell is a convex anticlockwise quadrangle with edges shorter than 1024 km
+    int filter_ok;              // the grid qualifies for the orientation filter of k_advect_warp (st_create checks)
     ProjConst proj;
     const AngEntry* atab;       // 47-entry angle table of inv_stere_fast (device)
 };
@@ -77,7 +79,7 @@ cudaError_t launch_advect_step(const AdvectGrid& g, const float* u, const float*
 cudaError_t launch_advect_ext(const AdvectGrid& g, const float* u, const float* v, const float* ic,
                               const BuoyState& s, int jrec, const StepOut& o, int scheme, int interp, int max_hops,
                               cudaStream_t st);
-cudaError_t launch_cell_bits(const AdvectGrid& g, int8_t* bits, cudaStream_t st);
+cudaError_t launch_cell_bits(const AdvectGrid& g, int8_t* bits, int* n_bad_coord, cudaStream_t st);
 cudaError_t launch_divcore(const double* a, const double* b, double* q_fast, double* q_div, long long n, cudaStream_t st);
 cudaError_t launch_div1000(const double* a, double* q_fast, double* q_div, long long n, cudaStream_t st);
 cudaError_t launch_advect_multi(const AdvectGrid& g, const float* rec0, long long rec_stride, int nrec,

@@ -6,6 +6,9 @@
 //   * a WARP owns its tiles of 32 buoys and its own shared-memory queue of crossings; appending is a
 //     ballot + popc, draining (32 entries, every lane busy) needs a __syncwarp only -- no CTA barrier, no
 //     counters; the alive count is one warp reduction and one atomic per warp at the end;
+//   * FILT 1: the inside test of the common path is an orientation filter (inside_margin, st_advect.cu) that
+//     certifies "inside" for lanes clear of every edge; the others are queued and the dense pass applies the
+//     reference's own test before walking -- the exact test runs on ~15 % of the buoys instead of all;
 //   * the row-store mode is a template parameter (ROWS 0: f8 rows into local HBM; 1: f4 rows and/or
 //     remote rows of the fused all-gather), so the default path carries no per-row mode branches.
 // Arithmetic, store addresses and results are those of k_advect_persist / k_advect_step_v1, bit for bit.
@@ -14,7 +17,7 @@
 
 namespace st {
 
-template <int UV, bool WIN, int ROWS, int BLK, int MINB>
+template <int UV, bool WIN, int ROWS, int FILT, int BLK, int MINB>
 __global__ void __launch_bounds__(BLK, MINB)
 k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __restrict__ v,
               const float* __restrict__ ic, BuoyState s, int jrec, StepOut o, int ntiles)
@@ -47,10 +50,18 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
             pt A, B;
             { const double2 q = *reinterpret_cast<const double2*>(&qP[wid][e]); A.y = q.x; A.x = q.y; }
             { const double2 q = *reinterpret_cast<const double2*>(&qPn[wid][e]); B.y = q.x; B.x = q.y; }
-            walk_cell(g, ic, A, B, cc.x, cc.y, a2);
-            const unsigned p = qI[wid][e];
-            if (cc.x != j0 || cc.y != i0) __stcs(s.cell + p, cc);
-            if (!a2) s.alive[p] = 0;
+            bool out = true;
+            if (FILT) {                                           // queued as "not certainly inside": the reference's test decides
+                const int c = cc.x * g.Ni + cc.y;
+                out = !inside_quad_flat(B.y, B.x, ldg_pt(g.F, c - g.Ni - 1), ldg_pt(g.F, c - g.Ni), ldg_pt(g.F, c),
+                                       ldg_pt(g.F, c - 1));
+            }
+            if (out) {
+                walk_cell(g, ic, A, B, cc.x, cc.y, a2);
+                const unsigned p = qI[wid][e];
+                if (cc.x != j0 || cc.y != i0) __stcs(s.cell + p, cc);
+                if (!a2) s.alive[p] = 0;
+            }
         }
         __syncwarp();                                             // slots may be overwritten again
     };
@@ -97,7 +108,9 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
         pt Pn;
         Pn.x = __dadd_rn(P.x, div1000(__dmul_rn(zU, g.rdt)));      // :452-458
         Pn.y = __dadd_rn(P.y, div1000(__dmul_rn(zV, g.rdt)));
-        const bool in = inside_quad2(Pn.y, Pn.x, bl, br, ur, ul, active);
+        bool in;
+        if (FILT) in = inside_margin(Pn.y, Pn.x, bl, br, ur, ul) && (__ldg(g.cellbits + c) & 4);   // same byte as the pick's
+        else      in = inside_quad2(Pn.y, Pn.x, bl, br, ur, ul, active);
         const bool cross = active && !in;
         pt outp = {ST_FILL, ST_FILL};
         int8_t m = 0;

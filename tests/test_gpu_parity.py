@@ -116,7 +116,7 @@ def test_track_golden(torch, corc, gold_track, name, multi):
     assert np.abs(ll - want).max() < LATLON_TOL_DEG                  # also for the -9999 rows (:493)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 4, 5, 6, 7, 8, 9, 10])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
 @pytest.mark.parametrize("name", list(TRACK_CASES))
 def test_track_golden_other_kernels(torch, corc, gold_track, name, variant):
     """v1 (straightforward), the other launch shapes of the tuned kernel and the persistent TMA/cp.async
@@ -355,6 +355,54 @@ def test_div1000_is_ieee_division(sit):
     assert np.array_equal(qf, qd)                                  # and so is the shortcut
 
 
+@pytest.mark.parametrize("case", ["far", "mangled"])
+def test_orientation_filter_fallbacks(torch, corc, gold_track, case):
+    """The default kernel certifies "inside" with an orientation filter and leaves everything else to the
+    reference's own test.  The filter must switch itself off where its error bound does not hold:
+    'far'     -- coordinates beyond 2^17 km (whole grid: st_create clears filter_ok);
+    'mangled' -- cells that are not convex anticlockwise quadrangles (per cell: k_cell_bits bit 2).
+    Either way trajectories, cells and alive flags stay those of the C oracle, bit for bit."""
+    T, g0 = gold_track
+    g = {k: np.array(v, copy=True) for k, v in g0.items()}
+    pos0 = T["pos0"].copy()
+    if case == "far":
+        for k in ("Xf", "Xu", "Xv", "Xt"):
+            if k in g:
+                g[k] = g[k] + 262144.0                         # 2^18 km east: exactly representable shift
+        pos0[:, 1] += 262144.0
+    else:
+        rng = np.random.default_rng(11)
+        Nj, Ni = g["tmask"].shape
+        jj, ii = rng.integers(3, Nj - 3, 60), rng.integers(3, Ni - 3, 60)
+        # drag corner points far enough to fold their four cells (concave, some clockwise)
+        g["Yf"][jj, ii] += rng.uniform(-1.2, 1.2, 60) * 12.5
+        g["Xf"][jj, ii] += rng.uniform(-1.2, 1.2, 60) * 12.5
+    nrec = 30
+    U, V, IC = 3 * T["U"][:nrec], 3 * T["V"][:nrec], T["IC"][:nrec]
+    ref = corc.track(g, U, V, IC, pos0, T["jiT0"].astype(np.int64), do_latlon=False)
+    assert ref["ncross"] > 100
+    dev = torch.device("cuda", 0)
+    nP = pos0.shape[0]
+    for variant in (0, 3):
+        with engine_for(g) as eng:
+            eng.set_kernel_variant(variant)
+            eng.set_buoys(pos0, T["jiT0"])
+            eng.record_slots(1)
+            yx = torch.empty((nP, 2), dtype=torch.float64, device=dev)
+            mk = torch.empty((nP,), dtype=torch.int8, device=dev)
+            for k in range(nrec):
+                st = eng.staging(0)
+                torch.cuda.synchronize()
+                st[0], st[1], st[2] = U[k], V[k], IC[k]
+                eng.submit_record(0)
+                eng.step(0, k, yx, None, mk, None)
+                torch.cuda.synchronize()
+                assert np.array_equal(yx.cpu().numpy(), ref["posC"][k + 1]), (case, variant, k)
+                assert np.array_equal(mk.cpu().numpy(), ref["mask"][k + 1])
+            p, c, a = eng.get_state()
+            assert np.array_equal(c, ref["jiT"]) and np.array_equal(a, ref["alive"])
+
+
 @pytest.mark.parametrize("preset,n,nrec,scale", [("nanuk4", 200_000, 30, 2.0), ("arctic12", 400_000, 16, 1.0)])
 def test_large_cloud_tuned_vs_v1_vs_oracle(torch, corc, preset, n, nrec, scale):
     """Dense clouds (many buoys per warp leaving their cell, kills, domain edges): the tuned kernel,
@@ -372,7 +420,7 @@ def test_large_cloud_tuned_vs_v1_vs_oracle(torch, corc, preset, n, nrec, scale):
     ref = corc.track(g, U, V, IC, pos0, cell0.astype(np.int64), history=False)
     assert ref["ncross"] > 0.02 * ik.size * nrec and ref["alive"].sum() < ik.size
     dev = torch.device("cuda", 0)
-    for variant in (0, 1, 4, 6, 8):
+    for variant in (0, 1, 3, 4, 6, 8):
         with engine_for(g) as eng:
             eng.set_kernel_variant(variant)
             eng.set_buoys(pos0, cell0)
