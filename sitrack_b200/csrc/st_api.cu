@@ -87,11 +87,11 @@ static double proj_akm1(double lat_ts_deg, double e)
 
 // Geodetic latitude as a function of t = tan(pi/4 - chi/2) on 0 <= t <= 1/2 (lat >~ 37N):
 // phi - pi/2 is odd in t, so phi = pi/2 + t Q(w), w = 8 t^2 - 1 in [-1,1].  Q is analytic with its
-// nearest singularity at w = -9, so its Chebyshev coefficients fall like 17.9^-k: degree 11 leaves
-// < 1e-15.  Coefficient generation (host, long double), like the angle table: not tracking arithmetic.
-static void fit_lat_poly(double e_, double out[12])
+// nearest singularity at w = -9, so its Chebyshev coefficients fall like 17.9^-k: degree 8 leaves
+// 1.7e-13 rad = 1e-11 degrees (degree 11: 5e-17 rad).  Coefficient generation (host, long double), like the angle table: not tracking arithmetic.
+static void fit_lat_poly(double e_, double out[ST_LAT_DEG + 1])
 {
-    const int N = 12, M = 32;
+    const int N = ST_LAT_DEG + 1, M = 32;
     const long double e = e_, PI_L = 3.14159265358979323846264338327950288L;
     long double c[N] = {0};
     for (int j = 0; j < M; ++j) {
@@ -136,9 +136,9 @@ static ProjConst make_proj(double lat_ts, double lon0)
     p.c[5] = 601676. / 22275 * n6;
     p.lon0_rad = lon0 * 0.017453292519943295;
     p.fill_lat = p.fill_lon = 0.0;
-    fit_lat_poly(e, p.lat_poly);
     const double R2D = 57.29577951308232, PI = 3.141592653589793;
-    for (int k = 0; k < 12; ++k) p.lat_poly_deg[k] = p.lat_poly[k] * R2D;
+    fit_lat_poly(e, p.lat_poly_deg);
+    for (int k = 0; k <= ST_LAT_DEG; ++k) p.lat_poly_deg[k] *= R2D;
     p.w_scale = 8.0 * p.k_t * p.k_t;
     // octant tables of inv_stere_fast (st_device.cuh: folded_angle): angle = sign * (off + sg * theta)
     const double off4[4] = {0.0, PI / 2, PI, PI / 2}, sg4[4] = {1.0, -1.0, -1.0, 1.0};
@@ -213,8 +213,8 @@ static cudaError_t refresh_fill(st_ctx* c)
 
 static cudaError_t make_angle_table(AngEntry** dst)
 {
-    std::vector<AngEntry> t(47);
-    for (int j = 0; j < 47; ++j) { const double a = j / 64.0; t[j].alpha = asin(a); t[j].ca = sqrt(1.0 - a * a); t[j].sa = a; t[j].pad = 0.0; }
+    std::vector<AngEntry> t(ST_ANG_LAST + 1);
+    for (int j = 0; j <= ST_ANG_LAST; ++j) { const double a = j / (double)ST_ANG_STEPS; t[j].alpha = asin(a); t[j].ca = sqrt(1.0 - a * a); t[j].sa = a; t[j].pad = 0.0; }
     return upload(dst, t.data(), t.size());
 }
 

@@ -138,15 +138,17 @@ __device__ __forceinline__ bool killed(int jT, int iT, int Nj, int Ni,
 // with sin/cos of 2*chi obtained algebraically from t: one atan and one atan2
 // per point instead of ~25 transcendentals.  Not bit-comparable with PROJ by
 // construction (PROJ itself stops at 1e-10); tolerance in tests: 1e-9 degrees.
+#define ST_LAT_DEG 8              // degree of the latitude polynomial: |error| < 2e-13 rad = 1e-11 degrees
+#define ST_ANG_STEPS 64           // angle table: alpha_j = asin(j / ST_ANG_STEPS), j = 0 .. ST_ANG_LAST
+#define ST_ANG_LAST 46            // > 64 / sqrt(2)
 struct ProjConst {
     double k_t;        // 1000 / (a * akm1): km radius -> t = tan(pi/4 - chi/2)
     double c[6];       // series coefficients of sin(2k chi), k = 1..6
     double lon0_rad;   // central longitude
     double fill_lat, fill_lon;   // inv_stere of (-9999,-9999) km: what rows of idle buoys hold (:493)
-    double lat_poly[12];         // phi = pi/2 + t * sum_k lat_poly[k] (8 t^2 - 1)^k for t <= 1/2
     // inv_stere_fast works in degrees from the start:
     double w_scale;              // 8 k_t^2: w = 8 t^2 - 1 = r^2 w_scale - 1
-    double lat_poly_deg[12];     // lat_poly in degrees: lat = 90 + t * sum_k lat_poly_deg[k] w^k
+    double lat_poly_deg[ST_LAT_DEG + 1];   // lat = 90 + t * sum_k lat_poly_deg[k] w^k for t <= 1/2 (lat >~ 37N)
     double oct_off[8], oct_sg[8];   // lon = oct_off[o] + oct_sg[o] * theta, o = swap | (cos<0)<<1 | (sin<0)<<2,
                                     // theta in [0, pi/4] the octant-folded angle; central longitude included
     int wrap_up;                 // lon0 > 0: only lon > 180 can occur; else only lon < -180
@@ -174,9 +176,10 @@ __device__ __forceinline__ pt inv_stere(pt yx, const ProjConst& pc)
 }
 
 // ---- fast inverse for the fused step (same map as inv_stere, fewer FP64-pipe slots) ------
-// angle of a unit vector from a 47-entry table: the octant-folded sine m = min(|s|,|c|) selects
-// alpha_j = asin(j/64); the remainder delta (|delta| < 0.011) comes from sin(delta) =
-// m cos(alpha_j) - M sin(alpha_j) and a 4-term asin series (error < 1e-19 rad).
+// angle of a unit vector from a 47-entry table (1.5 KB: a 183-entry table with a shorter series put 8 % of the
+// kernel's stall samples on the lookup): the octant-folded sine m = min(|s|,|c|) selects alpha_j = asin(j/64);
+// the remainder delta (|delta| < 0.011) comes from sin(delta) = m cos(alpha_j) - M sin(alpha_j) and three terms
+// of the asin series (error < 1e-15 rad).
 struct __align__(16) AngEntry { double alpha, ca, sa, pad; };
 
 // One Newton step on the MUFU seeds (~2^-20): relative error ~1e-12.  Enough here: both angle
@@ -204,13 +207,13 @@ __device__ __forceinline__ double folded_angle(double s, double c, const AngEntr
 {
     const bool swp = fabs(s) > fabs(c);
     const double ms = swp ? c : s, Ms = swp ? s : c;           // signed; magnitudes taken at the uses
-    int j = __double2int_rn(fabs(ms) * 64.0);
-    j = min(max(j, 0), 46);
+    int j = __double2int_rn(fabs(ms) * (double)ST_ANG_STEPS);
+    j = min(max(j, 0), ST_ANG_LAST);
     const double2 e0 = __ldg(reinterpret_cast<const double2*>(tab + j));          // alpha, cos
     const double sa = __ldg(reinterpret_cast<const double*>(tab + j) + 2);         // sin
-    const double sd = fma(fabs(ms), e0.y, -(fabs(Ms) * sa));
+    const double sd = fma(fabs(ms), e0.y, -(fabs(Ms) * sa));                      // sin(delta), |delta| < 0.011
     const double z = sd * sd;
-    const double d = fma(sd * z, fma(z, fma(z, 15. / 336., 3. / 40.), 1. / 6.), sd);
+    const double d = fma(sd * z, fma(z, 3. / 40., 1. / 6.), sd);                  // asin: next term 15/336 sd^7 < 1e-15 rad
     oct = (int)swp | ((int)(c < 0.0) << 1) | ((__double2hiint(s) >> 31) & 1) << 2;
     return e0.x + d;
 }
@@ -233,11 +236,11 @@ __device__ __forceinline__ pt inv_stere_fast(pt yx, const ProjConst& pc, const A
     const double w = fma(r2, pc.w_scale, -1.0);                    // 8 t^2 - 1
     pt r;
     if (w <= 1.0) {
-        // latitudes above ~37N: phi - pi/2 is odd in t, phi = pi/2 + t Q(8 t^2 - 1) with Q a degree-11
-        // polynomial fitted at st_create for the ellipsoid (|error| < 1e-14 rad, see make_proj)
-        double q = pc.lat_poly_deg[11];
+        // latitudes above ~37N: phi - pi/2 is odd in t, phi = pi/2 + t Q(8 t^2 - 1) with Q a degree-8
+        // polynomial fitted at st_create for the ellipsoid (|error| < 2e-13 rad = 1e-11 degrees, see make_proj)
+        double q = pc.lat_poly_deg[ST_LAT_DEG];
 #pragma unroll
-        for (int k = 10; k >= 0; --k) q = fma(q, w, pc.lat_poly_deg[k]);
+        for (int k = ST_LAT_DEG - 1; k >= 0; --k) q = fma(q, w, pc.lat_poly_deg[k]);
         r.y = fma(t, q, 90.0);
     } else {
         const double t2 = t * t;
