@@ -278,7 +278,7 @@ def run_ours(args):
     # roofline of the dominant kernel on THIS rank: algorithmic bytes / its mean launch duration.
     # The K launches run back to back on one stream, so the event span / K is the launch duration.
     achieved = (bsteps / K) * B_ALG / (ms / K * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_advect_step_v1<1,false>" if args.kernel == "v1" else ("k_advect_warp<1,false,0,32,32>" if args.kernel == "tuned" else "step variant %s" % args.kernel), "achieved": round(achieved, 1), "peak": peak,
+    roof = {"bound": "hbm", "kernel": "k_advect_step_v1<1,false>" if args.kernel == "v1" else ("k_advect_warp<1,false,0,1,32,32>" if args.kernel == "tuned" else "step variant %s" % args.kernel), "achieved": round(achieved, 1), "peak": peak,
             "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload),
             "peak_source": peak_src, "alg_bytes_per_buoy_step": B_ALG,
             "buoy_steps_per_launch": bsteps / K, "us_per_launch": round(ms / K * 1e3, 2)}
