@@ -26,6 +26,15 @@ __device__ __forceinline__ unsigned long long l2_keep_policy()
     asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+// Debug builds (python -m sitrack_b200.build -DST_DEBUG_BOUNDS=1 -o lib_dbg.so; SITRACK_B200_LIB=lib_dbg.so):
+// the step kernels check every cell whose stencil they are about to gather against the grid and trap on a
+// violation (compute-sanitizer is not available on every pool).
+#ifdef ST_DEBUG_BOUNDS
+#define ST_CHECK_CELL(c, reach, Nj, Ni) do { const long long c_ = (c), r_ = (reach), n_ = (long long)(Nj) * (Ni); \
+                                             if (c_ - r_ < 0 || c_ + r_ >= n_) __trap(); } while (0)
+#else
+#define ST_CHECK_CELL(c, reach, Nj, Ni) do { } while (0)
+#endif
 __device__ __forceinline__ pt ldg_pt(const pt* __restrict__ a, int idx)
 {
     pt r;
@@ -121,6 +130,7 @@ __device__ __forceinline__ bool killed(int jT, int iT, int Nj, int Ni,
 {
     if (jT <= 1 || jT >= Nj - 2 || iT <= 1 || iT >= Ni - 2) return true;
     const int c = jT * Ni + iT;
+    ST_CHECK_CELL(c, Ni + 1, Nj, Ni);
     const int zmt = __ldg(tmask + c) + __ldg(tmask + c + 1) + __ldg(tmask + c + Ni) +
                     __ldg(tmask + c - 1) + __ldg(tmask + c - Ni - 1);          // sic: [jT-1,iT-1]
     if (zmt < 5) return true;

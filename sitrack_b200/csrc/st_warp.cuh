@@ -88,6 +88,7 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
         const int2 cw = active ? c2 : make_int2(2, 2);
         const int Ni = g.Ni;
         const int c = cw.x * Ni + cw.y;
+        ST_CHECK_CELL(c, Ni + 1, g.Nj, Ni);
         const pt bl = ldg_pt(g.F, c - Ni - 1), br = ldg_pt(g.F, c - Ni);
         const pt ul = ldg_pt(g.F, c - 1),      ur = ldg_pt(g.F, c);
         double zU, zV;
