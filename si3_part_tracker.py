@@ -9,7 +9,12 @@ loop (reference tracking.py:120-160) and the records x buoys loop
 Inputs may be netCDF (needs netCDF4) or the `.npz` equivalents described in
 sitrack_b200/ncio.py.  Plotting (-p) is accepted and ignored: the plotting stack (mojito,
 cartopy) is outside the scope of this path.
+
+Several GPUs: `torchrun --nproc-per-node N si3_part_tracker.py ...` (one process per GPU).  Rank 0 does the
+seeding stage; every rank then tracks its contiguous block of buoys (they never interact, reference :378-488)
+with its own replica of the grid and of each record, and rank 0 collects the rows and writes the files.
 """
+import os
 from os import path, makedirs
 from re import split
 from sys import exit
@@ -109,6 +114,11 @@ def main():
     print('#            SITRACK ICE PARTICULES TRACKER              #')
     print('#                 (sitrack_b200 engine)                  #')
     print('##########################################################\n')
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist                      # host-side plumbing only: gloo over CPU arrays
+        dist.init_process_group("gloo")
     args = __argument_parsing__()
     cf_uv, cf_mm, fNCseed, jrecSeed, cdate_stop, CONF = args.fsi3, args.fmmm, args.fsdg, args.krec, args.dend, args.ncnf
     lUse2DTime = not args.fxdt
@@ -144,6 +154,8 @@ def main():
 
     # ---- initialization / seeding (reference :205-255) ----------------------------------------
     cf_npz_itm = './seed/Initialized_buoys_' + SeedName + '_' + CONF + '.npz'
+    if world > 1 and rank != 0:
+        dist.barrier()                                            # rank 0 is locating the seeds / writing the cache
     if path.exists(cf_npz_itm):
         print('\n *** We found file ' + cf_npz_itm + ' here! So using it and skipping first stage!')
         with np.load(cf_npz_itm) as data:
@@ -164,9 +176,19 @@ def main():
         print('\n *** Saving intermediate data into ' + cf_npz_itm + '!')
         np.savez_compressed(cf_npz_itm, nP=nP, xPosG0=xPosG0, xPosC0=xPosC0, IDs=IDs, vJIt=vJIt, VRTCS=VRTCS, idxKeep=idxK)
 
+    if world > 1 and rank == 0:
+        dist.barrier()                                            # the cache is on disk: the other ranks may read it
+
     z1st = zLst = None
     if lUse2DTime:
         z1st, zLst = record_windows(zTpos, nP, kstrt, kstop, ztime_model, iTmA, iTmB)
+    lo, hi = 0, nP
+    if world > 1:
+        from sitrack_b200.dist import my_shard
+        lo, hi = my_shard(nP, rank, world)
+        print(' *** rank %d of %d tracks buoys [%d, %d) of %d' % (rank, world, lo, hi, nP))
+    sh = slice(lo, hi)
+    cut = lambda a: None if a is None else a[sh]
 
     # ---- the record loop on the GPU (reference :361-496) -----------------------------------------
     vTime = np.zeros(Nt + 1, dtype=int)
@@ -182,16 +204,27 @@ def main():
 
     eng = sit.TrackEngine(xYf, xXf, xYu, xXu, xYv, xXv, tmask=imaskt, uv_strategy=args.uvstrategy, rdt=rdt,
                           rmin_conc=sit.rmin_conc, device=sit.config.device)
-    eng.set_buoys(xPosC0, vJIt, z1st, zLst)
+    eng.set_buoys(xPosC0[sh], vJIt[sh], cut(z1st), cut(zLst))
     # rows come back in the file's dtype (every trajectory variable is f4, ncio.py:153-159)
     physics = None
     if args.scheme != 'euler' or args.interp != 'pick' or args.hops != 1:
         physics = dict(scheme={'euler': 1, 'rk2': 2, 'rk4': 4}[args.scheme], interp=int(args.interp == 'linear'), max_hops=args.hops)
         print(' *** NOTE: optional physics beyond upstream sitrack is ON:', physics)
-    res = eng.track(record, Nt, kstrt=kstrt, pos0=xPosC0, posG0=xPosG0, rec_first=z1st,
+    res = eng.track(record, Nt, kstrt=kstrt, pos0=xPosC0[sh], posG0=xPosG0[sh], rec_first=cut(z1st),
                     row_dtype='f8' if physics else args.rows, physics=physics)
     eng.close()
     ds.close()
+    if world > 1:
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(res, parts, dst=0)
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return 0
+        res = dict(posC=np.concatenate([p['posC'] for p in parts], axis=1),
+                   posG=np.concatenate([p['posG'] for p in parts], axis=1),
+                   mask=np.concatenate([p['mask'] for p in parts], axis=1),
+                   n_alive=np.sum([p['n_alive'] for p in parts], axis=0))
     xPosC, xPosG, xmask = res['posC'], res['posG'], res['mask']
     for jt in range(Nt):
         print('   *   record ' + str(jt + kstrt) + ': number of buoys alive = ' + str(int(res['n_alive'][jt])))

@@ -107,3 +107,33 @@ def test_readme_workflow_seeding_then_tracking(tmp_path, monkeypatch):
     assert len(out) == 1
     t = np.load(tmp_path / "nc" / out[0])
     assert t["y_pos"].shape[0] == 13 and t["mask"][0].all() and 0 < t["mask"][-1].sum() <= t["mask"].shape[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_cli_under_torchrun_shards_buoys_and_writes_the_same_files(tmp_path):
+    """`torchrun --nproc-per-node 2 si3_part_tracker.py ...`: rank 0 seeds, each rank tracks its block of buoys
+    (both on cuda:0 here, so the test runs on a one-GPU box), rank 0 writes the files -- identical to the
+    single-process run's, variable by variable."""
+    import socket
+    import subprocess
+    from make_synth_case import write_case
+    r = write_case(str(tmp_path / "in"), grid="small", nrec=12, hss=2)
+    cli = os.path.join(ROOT, "si3_part_tracker.py")
+    common = ["-i", r["si3"], "-m", r["mesh"], "-s", r["seed"], "-F", "-N", "SYNTH4", "--device", "0"]
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    one, two = tmp_path / "one", tmp_path / "two"
+    one.mkdir(); two.mkdir()
+    subprocess.run([sys.executable, cli] + common, cwd=one, env=env, check=True, stdout=subprocess.DEVNULL)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                    "--master-addr", "127.0.0.1", "--master-port", str(port), cli] + common,
+                   cwd=two, env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    files = sorted(os.listdir(one / "nc"))
+    assert files == sorted(os.listdir(two / "nc")) and len(files) == 2
+    for f in files:
+        a, b = np.load(one / "nc" / f), np.load(two / "nc" / f)
+        assert sorted(a.files) == sorted(b.files)
+        for k in a.files:
+            assert np.array_equal(a[k], b[k]), (f, k)
+        assert a["y_pos"].shape[1] > 256                       # more than one tile: both ranks had work
