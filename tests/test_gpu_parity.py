@@ -446,9 +446,11 @@ def test_large_cloud_tuned_vs_v1_vs_oracle(torch, corc, preset, n, nrec, scale):
 
 # ---- full season (BASELINE config 2) -------------------------------------------------------------------
 
-def test_full_season_config2_vs_oracle(torch, corc):
+@pytest.mark.parametrize("path", ["season", "per_record"])
+def test_full_season_config2_vs_oracle(torch, corc, path):
     """NANUK4-shaped grid, HSS5 seeding (~1k buoys), 3024 hourly records (1996-12-15 -> 1997-04-20), -F:
-    the chunked season path (k_advect_multi, 126 records per launch) against the C oracle, record
+    the chunked season path (k_advect_multi, 126 records per launch) and the per-record pipeline (the default
+    step kernel k_advect_warp, one launch per record, rows streamed back) against the C oracle, record
     by record.  Target of the north star: >= 95 % of buoys bit-exact in cell index over the season;
     measured: 100 %, with bit-identical f8 positions (accumulated divergence 0 km)."""
     import synth
@@ -472,7 +474,7 @@ def test_full_season_config2_vs_oracle(torch, corc):
                 cache[c] = synth.make_records(g, chunk, seed=1000 + c, k0=c * chunk)
             U, V, IC = cache[c]
             return U[k % chunk], V[k % chunk], IC[k % chunk]
-        r = eng.track(records, nrec, pos0=pos0, chunk=chunk)
+        r = eng.track(records, nrec, pos0=pos0, chunk=chunk if path == "season" else None)
         p_end, c_end, a_end = eng.get_state()
     pos, ji, alive = pos0.copy(), cell0.astype(np.int64), np.ones(ik.size, np.int8)
     same_cell = np.ones(ik.size, bool)
