@@ -177,7 +177,11 @@ static cudaError_t upload(T** dst, const T* src, size_t n)
 {
     cudaError_t e = cudaMalloc((void**)dst, n * sizeof(T));
     if (e != cudaSuccess) return e;
-    return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+    e = cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+    // a copy from pageable memory may return once the data is staged, before the DMA has landed; the kernels
+    // that follow run on non-blocking streams, which the legacy stream does not order: wait for it here
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
+    return e;
 }
 
 static bool g_coord_range_ok = true;
@@ -447,7 +451,10 @@ int st_find_containing_cell(st_ctx* c, int64_t n, const double* yx, const int32_
 }
 
 // ---- buoy state ----------------------------------------------------------------------------
-static int reserve_buoys(st_ctx* c, int64_t nP, bool window)
+// `s`: the stream the caller fills the state on.  The zero fill of fresh capacity must be ordered before that
+// fill: a cudaMemset on the legacy default stream is NOT ordered against a non-blocking stream and may land
+// after it (seen with two processes sharing a GPU: every buoy dead from the first record).
+static int reserve_buoys(st_ctx* c, int64_t nP, bool window, cudaStream_t s)
 {
     if (nP > c->capP) {
         cudaFree(c->pos); cudaFree(c->cell); cudaFree(c->alive); cudaFree(c->rec_first); cudaFree(c->rec_last);
@@ -457,9 +464,9 @@ static int reserve_buoys(st_ctx* c, int64_t nP, bool window)
         CU(c, cudaMalloc(&c->pos, sizeof(pt) * cap));
         CU(c, cudaMalloc(&c->cell, sizeof(int2) * cap));
         CU(c, cudaMalloc(&c->alive, (size_t)cap));
-        CU(c, cudaMemset(c->pos, 0, sizeof(pt) * cap));
-        CU(c, cudaMemset(c->cell, 0, sizeof(int2) * cap));
-        CU(c, cudaMemset(c->alive, 0, (size_t)cap));
+        CU(c, cudaMemsetAsync(c->pos, 0, sizeof(pt) * cap, s));
+        CU(c, cudaMemsetAsync(c->cell, 0, sizeof(int2) * cap, s));
+        CU(c, cudaMemsetAsync(c->alive, 0, (size_t)cap, s));
         c->capP = cap;
     }
     if (window && !c->rec_first) {
@@ -478,7 +485,7 @@ static int set_buoys_impl(st_ctx* c, int64_t nP, const double* pos, const int32_
     CU(c, cudaSetDevice(c->device));
     c->nP = 0;
     if (nP > 0) {
-        int rc = reserve_buoys(c, nP, rf != nullptr);
+        int rc = reserve_buoys(c, nP, rf != nullptr, s);
         if (rc) return rc;
         CU(c, cudaMemcpyAsync(c->pos, pos, sizeof(pt) * nP, kind, s));
         CU(c, cudaMemcpyAsync(c->cell, cell, sizeof(int2) * nP, kind, s));
@@ -730,6 +737,7 @@ int st_gather_create(st_ctx* c, int rank, int world, int64_t nP_total, int64_t o
     g.block_bytes = g.flags_off + GA_FLAG_BYTES;
     CU(c, cudaMalloc(&g.base, g.block_bytes));
     CU(c, cudaMemset(g.base + g.flags_off, 0, GA_FLAG_BYTES));
+    CU(c, cudaDeviceSynchronize());                       // default-stream memset: not ordered against the callers' non-blocking streams
     g.peer[rank] = g.base;
     if (handle_out) {
         cudaIpcMemHandle_t h;
