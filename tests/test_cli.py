@@ -137,3 +137,29 @@ def test_cli_under_torchrun_shards_buoys_and_writes_the_same_files(tmp_path):
         for k in a.files:
             assert np.array_equal(a[k], b[k]), (f, k)
         assert a["y_pos"].shape[1] > 256                       # more than one tile: both ranks had work
+
+
+@pytest.mark.gpu
+def test_cli_optional_physics_flags(tmp_path, monkeypatch):
+    """--scheme/--interp/--hops route the record loop through st_step_ext: same files and layout, trajectories
+    close to the upstream Euler/face-pick ones but not equal (12 records, displacements of a few km)."""
+    import si3_part_tracker as cli
+    from make_synth_case import write_case
+    r = write_case(str(tmp_path / "in"), grid="small", nrec=12, hss=3)
+    outs = {}
+    for tag, extra in (("euler", []), ("rk4", ["--scheme", "rk4", "--interp", "linear", "--hops", "4"])):
+        d = tmp_path / tag
+        d.mkdir()
+        monkeypatch.chdir(d)
+        monkeypatch.setattr(sys, "argv", ["si3_part_tracker.py", "-i", r["si3"], "-m", r["mesh"], "-s", r["seed"],
+                                          "-F", "-N", "SYNTH4"] + extra)
+        quiet(cli.main)
+        f = [f for f in os.listdir(d / "nc") if "_tracking_" in f]
+        assert len(f) == 1
+        outs[tag] = np.load(d / "nc" / f[0])
+    a, b = outs["euler"], outs["rk4"]
+    assert a["y_pos"].shape == b["y_pos"].shape and np.array_equal(a["y_pos"][0], b["y_pos"][0])
+    both = (a["mask"][-1] == 1) & (b["mask"][-1] == 1)
+    assert both.mean() > 0.8
+    d = np.hypot(a["y_pos"][-1][both] - b["y_pos"][-1][both], a["x_pos"][-1][both] - b["x_pos"][-1][both])
+    assert 0.0 < d.max() < 5.0 and np.median(d) < 1.0            # km
