@@ -143,3 +143,40 @@ def test_ext_reference_settings_track_the_bit_exact_step(torch, gold_track):
             live = same & (T["uv1_mask"][k + 1] == 1)
             assert np.abs(got[live] - want[live]).max() < 1e-9
         assert same.mean() > 0.9, same.mean()
+
+
+@pytest.mark.parametrize("scheme,interp,hops,uv", [(2, 1, 4, 1), (4, 1, 4, 1), (1, 0, 3, 1), (4, 0, 2, 1), (2, 0, 2, 0)])
+def test_ext_modes_on_a_curvilinear_grid_vs_numpy_restatement(torch, gold_track, scheme, interp, hops, uv):
+    """On the warped golden grid (no closed form) the kernel must follow oracle/ext_ref.py -- an independent
+    numpy restatement of the same definitions -- record by record: positions to 1e-9 km, cells and alive
+    flags exactly.  3x faster ice than the golden run, so multi-cell moves, stage walks and kills all occur."""
+    from oracle import ext_ref
+    T, g = gold_track
+    nrec, nP = 20, T["pos0"].shape[0]
+    U, V, IC = 3 * T["U"][:nrec], 3 * T["V"][:nrec], T["IC"][:nrec]
+    pos, cell, alive = T["pos0"].copy(), T["jiT0"].astype(np.int64).copy(), np.ones(nP, np.int8)
+    dev = torch.device("cuda", 0)
+    moved = 0
+    with engine_for(g, uv_strategy=uv) as eng:
+        eng.set_buoys(T["pos0"], T["jiT0"])
+        eng.record_slots(1)
+        yx = torch.empty((nP, 2), dtype=torch.float64, device=dev)
+        mk = torch.empty((nP,), dtype=torch.int8, device=dev)
+        for k in range(nrec):
+            st = eng.staging(0)
+            torch.cuda.synchronize()
+            st[0], st[1], st[2] = U[k], V[k], IC[k]
+            eng.submit_record(0)
+            eng.step_ext(0, k, scheme, interp, hops, yx, None, mk, None)
+            torch.cuda.synchronize()
+            c_before = cell.copy()
+            want_yx, want_mk = ext_ref.step(g, U[k], V[k], IC[k], pos, cell, alive, scheme, interp, hops, uv_strategy=uv)
+            moved += int((c_before != cell).any(axis=1).sum())
+            got = yx.cpu().numpy()
+            assert np.array_equal(mk.cpu().numpy(), want_mk), k
+            live = want_mk == 1
+            assert np.abs(got[live] - want_yx[live]).max() < 1e-9, k
+            assert np.array_equal(got[~live], want_yx[~live])
+            p, c, a = eng.get_state()
+            assert np.array_equal(c, cell) and np.array_equal(a, alive), k
+    assert moved > 50 and alive.sum() < nP
