@@ -77,3 +77,18 @@ def test_against_reference_host_functions():
     dat = os.path.join(os.path.dirname(os.path.dirname(ref.__file__)), "tools", "sidfexloc.dat")
     ll, ids = quiet(sit.SidfexSeeding, dat); ll2, ids2 = quiet(ref.SidfexSeeding, dat)
     assert np.array_equal(ll, ll2) and np.array_equal(ids, ids2)
+
+
+def test_row_dtype_selection_and_numa_binding_helpers():
+    """Host plumbing added with the f4 rows and the multi-GPU paths: the row-buffer dtype picks the C entry
+    point (mixing raises before any launch), and the NUMA binding degrades to None without NVML / a GPU."""
+    import numpy as np
+    from sitrack_b200.engine import _rows_f4
+    from sitrack_b200.dist import bind_host_to_gpu, shard_bounds
+    a8, a4 = np.zeros((3, 2)), np.zeros((3, 2), np.float32)
+    assert _rows_f4(None, None) is False and _rows_f4(a8, None) is False and _rows_f4(a4, a4) is True
+    with pytest.raises(TypeError):
+        _rows_f4(a4, a8)
+    assert bind_host_to_gpu(10 ** 6) is None                     # no such device: no binding, no exception
+    b = shard_bounds(636, 2)                                     # the CLI's torchrun test: 512 + 124 buoys
+    assert b.tolist() == [0, 512, 636]
