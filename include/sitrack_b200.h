@@ -56,12 +56,13 @@ int  st_create(st_ctx **out, int device, int Nj, int Ni,
 void st_destroy(st_ctx *ctx);
 
 /* Step-kernel variant, all bit-identical in their results:
- *   0 (default) k_advect_warp 32x32: tuned step, persistent, every warp owns its tiles and its own
- *     shared-memory queue of cell crossings (no CTA barrier); 2 / 5 the same at 64x16 / 128x8; 3 = 0;
- *   6 / 7 / 10 / 11 k_advect_persist, the same step with one walk queue per CTA (64x16 / 128x8 / 64x18 / 64x20);
- *   4 / 9 k_advect_step, the tuned step with one block per tile (128x10 / 256x4);
+ *   0 (default) k_advect_cert: persistent one-warp CTAs; U/V pick and inside test decided from a 36-byte
+ *     per-cell frame in f32 when provably equal to the reference's tests, the reference's own tests in dense
+ *     passes over queued buoys otherwise (csrc/st_cert.cuh);
  *   1 k_advect_step_v1, the straightforward kernel (also SITRACK_B200_KERNEL=v1);
- *   8 k_advect_pipe, persistent CTAs with a TMA state ring and cp.async gathers.               */
+ *   2 k_advect_warp (round-1 default: full f8 geometry gathers, orientation filter for the inside test), 3 the
+ *     same with the reference's inside test on every lane;
+ *   4, 6-11 round-1 experiments, present only in -DST_EXPERIMENTS builds (ST_EINVAL otherwise).             */
 int  st_set_kernel_variant(st_ctx *ctx, int variant);
 
 /* Polar-stereographic parameters of CartNPSkm2Geo1D (util.py:413: lat0=70, lon0=-45). */
@@ -95,7 +96,11 @@ int  st_find_containing_cell(st_ctx *ctx, int64_t n, const double *yx, const int
 /* ---- buoy state (xPosC[jt], vJIt, iAlive; si3_part_tracker.py:324-344) ----------------
  * pos (nP,2) [y,x] km, cell (nP,2).  rec_first/rec_last (nP) are the per-buoy model
  * record windows z1stModelRec/zLstModelRec (:264-312); pass NULL for -F runs.  All
- * buoys start alive.  *_dev variants take device pointers and copy device-to-device.    */
+ * buoys start alive, except those whose cell lies outside [2,Nj-3] x [2,Ni-3] (Survive's first
+ * test, tracking.py:73-76, would discontinue them on entry; the step gathers their stencil
+ * unclamped): they start discontinued.  *_dev variants take device pointers and copy
+ * device-to-device.  On the DEVICE a discontinued buoy also carries bit 31 in the jT word of
+ * its cell (st_state_device_ptrs shows that encoding; st_get_state strips it).               */
 int  st_set_buoys(st_ctx *ctx, int64_t nP, const double *pos, const int32_t *cell,
                   const int32_t *rec_first, const int32_t *rec_last);
 int  st_set_buoys_dev(st_ctx *ctx, int64_t nP, const double *pos_dev, const int32_t *cell_dev,
@@ -249,6 +254,22 @@ int  st_selftest_div1000(int device, int64_t n, const double *a, double *q_fast,
 /* Same for the branch-free general division of the inside test (locate.py:72): q_fast = the
  * kernel's nine-operation sequence, q_div = IEEE division, for n host pairs a/b.            */
 int  st_selftest_divide(int device, int64_t n, const double *a, const double *b, double *q_fast, double *q_div);
+
+/* Diagnostics of the certified fast path of the default step kernel (csrc/st_cert.cuh).  The kernel decides the
+ * U/V pick (si3_part_tracker.py:430-441) and "still inside its cell" (locate.py:49-78) from a per-cell affine
+ * frame in f32 whenever the buoy is farther than proven margins from every line involved, and runs the
+ * reference's own tests otherwise.
+ *   st_cert_stats     cells admitted to the fast path / cells examined (0/0 when the grid has no frames).
+ *   st_cert_frames    host copies of the frames ((Nj,Ni,8) f32: oy ox a b c d es et) and of the packed margins
+ *                     ((Nj,Ni) u32: bf16(hin) << 16 | bf16(msep)); either may be NULL.
+ *   st_selftest_cert  for n host triples (position yx (n,2), host cell (n,2), face velocities vel4 (n,4) f4 =
+ *                     uL uR vB vT) returns flags (n) u8: bit0 pick certified, bit1 stay certified, bit2/bit3 the
+ *                     certified llum1/llvm1, bit4/bit5 the reference's llum1/llvm1, bit6 the reference's
+ *                     IsInsideQuadrangle of the reference's new position.                                        */
+int  st_cert_stats(st_ctx *ctx, int64_t *admitted, int64_t *examined);
+int  st_cert_frames(st_ctx *ctx, float *frames, uint32_t *margins);
+int  st_selftest_cert(st_ctx *ctx, int64_t n, const double *yx, const int32_t *cell, const float *vel4,
+                      uint8_t *flags);
 
 #ifdef __cplusplus
 }

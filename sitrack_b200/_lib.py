@@ -33,6 +33,9 @@ SIGNATURES = {
     "st_selftest_xy2latlon_fast": (c_int, [c_int, c_i64, vp, vp, c_dbl, c_dbl]),
     "st_selftest_div1000": (c_int, [c_int, c_i64, vp, vp, vp]),
     "st_selftest_divide": (c_int, [c_int, c_i64, vp, vp, vp, vp]),
+    "st_cert_stats": (c_int, [vp, C.POINTER(c_i64), C.POINTER(c_i64)]),
+    "st_cert_frames": (c_int, [vp, vp, vp]),
+    "st_selftest_cert": (c_int, [vp, c_i64, vp, vp, vp, vp]),
     "st_set_locate_grid": (c_int, [vp, vp, vp, vp]),
     "st_seed_locate": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp]),
     "st_seed_locate_dev": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp]),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libsitrack_b200.so")
 SOURCES = ["st_api.cu", "st_advect.cu", "st_locate.cu", "st_geom.cu", "st_ext.cu"]
-HEADERS = ["st_device.cuh", "st_kernels.h", "st_persist.cuh", "st_pipe.cuh", "st_warp.cuh", os.path.join("..", "..", "include", "sitrack_b200.h")]
+HEADERS = ["st_device.cuh", "st_kernels.h", "st_persist.cuh", "st_pipe.cuh", "st_warp.cuh", "st_cert.cuh", "st_experiments.cuh", os.path.join("..", "..", "include", "sitrack_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -27,6 +27,8 @@ struct st_ctx {
     pt *F = nullptr, *U = nullptr, *V = nullptr;
     int8_t* tmask = nullptr;
     int8_t* cellbits = nullptr;
+    float4* frames = nullptr; unsigned* fmargin = nullptr;      // certified fast path (k_cell_frames)
+    unsigned long long frame_stats[2] = {0, 0};                 // cells admitted / examined
     double *latT = nullptr, *lonT = nullptr, *resKM = nullptr;
     int *bin_start = nullptr, *bin_pts = nullptr;
     AngEntry* atab = nullptr;
@@ -35,6 +37,7 @@ struct st_ctx {
     // buoys
     long long nP = 0, capP = 0;
     pt* pos = nullptr; int2* cell = nullptr; int8_t* alive = nullptr;
+    unsigned long long* n_bad_cell = nullptr;                   // buoys st_set_buoys discontinued for an out-of-range cell
     int32_t *rec_first = nullptr, *rec_last = nullptr;
     bool has_window = false;
     int variant = 0;            // st_set_kernel_variant: 0 = k_advect_warp (default), 1 = k_advect_step_v1, ...
@@ -283,6 +286,20 @@ int st_create(st_ctx** out, int device, int Nj, int Ni, const double* Yf, const 
         // the orientation filter's error bound assumes km coordinates within 2^17 (inside_margin)
         c->grid.filter_ok = (bad == 0) && !getenv("SITRACK_B200_NO_FILTER");
     }
+    // frames and margins of the certified fast path (k_advect_cert); SITRACK_B200_NO_CERT=1 keeps the round-1 default
+    if (e == cudaSuccess && c->grid.filter_ok && !getenv("SITRACK_B200_NO_CERT")) {
+        unsigned long long* d_stats = nullptr;
+        e = cudaMalloc(&c->frames, sizeof(float4) * 2 * n);
+        if (e == cudaSuccess) e = cudaMalloc(&c->fmargin, sizeof(unsigned) * n);
+        if (e == cudaSuccess) e = cudaMalloc(&d_stats, 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), c->stream);
+        if (e == cudaSuccess) e = launch_cell_frames(c->grid, c->frames, c->fmargin, d_stats, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->frame_stats, d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(d_stats);
+        c->grid.frames = c->frames; c->grid.fmargin = c->fmargin;
+        c->grid.frames_ok = (e == cudaSuccess);
+    }
     if (e != cudaSuccess) { rc = cuda_fail(nullptr, e, "st_create(projection tables, cell bits)"); st_destroy(c); return rc; }
     { const char* ev = getenv("SITRACK_B200_KERNEL"); if (ev && ev[0] == 'v' && ev[1] == '1') c->variant = 1; }
     *out = c;
@@ -291,7 +308,12 @@ int st_create(st_ctx** out, int device, int Nj, int Ni, const double* Yf, const 
 
 int st_set_kernel_variant(st_ctx* c, int variant)
 {
-    if (!c || variant < 0 || variant > 11) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 warp-private tuned (default; 2/3/5 other shapes), 1 v1, 4/9 one-block-per-tile tuned, 6/7/10/11 CTA-queue persistent, 8 TMA pipelined");
+#ifdef ST_EXPERIMENTS
+    const bool known = variant >= 0 && variant <= 11 && variant != 5;
+#else
+    const bool known = variant >= 0 && variant <= 3;
+#endif
+    if (!c || !known) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 certified fast path (default), 1 v1, 2 warp-private with orientation filter, 3 warp-private exact; 4, 6-11 only in -DST_EXPERIMENTS builds");
     c->variant = variant;
     return ST_OK;
 }
@@ -300,9 +322,9 @@ void st_destroy(st_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->F); cudaFree(c->U); cudaFree(c->V); cudaFree(c->tmask); cudaFree(c->atab); cudaFree(c->cellbits);
+    cudaFree(c->F); cudaFree(c->U); cudaFree(c->V); cudaFree(c->tmask); cudaFree(c->atab); cudaFree(c->cellbits); cudaFree(c->frames); cudaFree(c->fmargin);
     cudaFree(c->latT); cudaFree(c->lonT); cudaFree(c->resKM); cudaFree(c->bin_start); cudaFree(c->bin_pts);
-    cudaFree(c->pos); cudaFree(c->cell); cudaFree(c->alive); cudaFree(c->rec_first); cudaFree(c->rec_last);
+    cudaFree(c->pos); cudaFree(c->cell); cudaFree(c->alive); cudaFree(c->rec_first); cudaFree(c->rec_last); cudaFree(c->n_bad_cell);
     cudaFree(c->o_yx); cudaFree(c->o_ll); cudaFree(c->o_mask); cudaFree(c->o_nalive);
     for (float* p : c->d_rec) cudaFree(p);
     for (float* p : c->h_rec) cudaFreeHost(p);
@@ -425,6 +447,22 @@ __global__ void k_find_cell(const AdvectGrid g, long long n, const pt* __restric
 }
 }  // namespace st
 
+namespace st {
+// set_buoys: a buoy whose cell lies outside [2,Nj-3] x [2,Ni-3] would fail Survive's first test
+// (tracking.py:73-76) the moment it entered that cell; the step kernels gather its stencil unclamped, so such
+// a buoy (stale or foreign Initialized_buoys_*.npz, API misuse) starts discontinued instead of faulting.
+__global__ void k_init_alive(long long nP, int Nj, int Ni, int2* __restrict__ cell, int8_t* __restrict__ alive,
+                             unsigned long long* __restrict__ n_bad)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nP) return;
+    int2 c = cell[p];
+    const bool ok = c.x >= 2 && c.x <= Nj - 3 && c.y >= 2 && c.y <= Ni - 3;
+    if (!ok) { c.x = (c.x & ~ST_DEAD_BIT) | ST_DEAD_BIT; cell[p] = c; atomicAdd(n_bad, 1ull); }
+    alive[p] = ok ? 1 : 0;
+}
+}  // namespace st
+
 extern "C" {
 
 int st_find_containing_cell(st_ctx* c, int64_t n, const double* yx, const int32_t* ji_near, int32_t* cell, int8_t* found)
@@ -489,7 +527,10 @@ static int set_buoys_impl(st_ctx* c, int64_t nP, const double* pos, const int32_
         if (rc) return rc;
         CU(c, cudaMemcpyAsync(c->pos, pos, sizeof(pt) * nP, kind, s));
         CU(c, cudaMemcpyAsync(c->cell, cell, sizeof(int2) * nP, kind, s));
-        CU(c, cudaMemsetAsync(c->alive, 1, (size_t)nP, s));
+        if (!c->n_bad_cell) CU(c, cudaMalloc(&c->n_bad_cell, sizeof(unsigned long long)));
+        CU(c, cudaMemsetAsync(c->n_bad_cell, 0, sizeof(unsigned long long), s));
+        k_init_alive<<<(unsigned)((nP + 255) / 256), 256, 0, s>>>(nP, c->Nj, c->Ni, c->cell, c->alive, c->n_bad_cell);
+        CU(c, cudaGetLastError());
         if (rf) {
             CU(c, cudaMemcpyAsync(c->rec_first, rf, sizeof(int32_t) * nP, kind, s));
             CU(c, cudaMemcpyAsync(c->rec_last, rl, sizeof(int32_t) * nP, kind, s));
@@ -521,7 +562,10 @@ int st_get_state(st_ctx* c, double* pos, int32_t* cell, int8_t* alive)
     CU(c, cudaDeviceSynchronize());
     if (c->nP == 0) return ST_OK;
     if (pos) CU(c, cudaMemcpy(pos, c->pos, sizeof(pt) * c->nP, cudaMemcpyDeviceToHost));
-    if (cell) CU(c, cudaMemcpy(cell, c->cell, sizeof(int2) * c->nP, cudaMemcpyDeviceToHost));
+    if (cell) {
+        CU(c, cudaMemcpy(cell, c->cell, sizeof(int2) * c->nP, cudaMemcpyDeviceToHost));
+        for (long long k = 0; k < c->nP; ++k) cell[2 * k] &= 0x7fffffff;       // bit 31 = discontinued (device encoding)
+    }
     if (alive) CU(c, cudaMemcpy(alive, c->alive, (size_t)c->nP, cudaMemcpyDeviceToHost));
     return ST_OK;
 }
@@ -1004,6 +1048,44 @@ int st_selftest_divide(int device, int64_t n, const double* a, const double* b, 
     CUS(launch_divcore(da, db, f, r, n, 0));
     CUS(cudaMemcpy(q_fast, f, sizeof(double) * n, cudaMemcpyDeviceToHost));
     CUS(cudaMemcpy(q_div, r, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_cert_stats(st_ctx* c, int64_t* admitted, int64_t* examined)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (admitted) *admitted = c->grid.frames_ok ? (int64_t)c->frame_stats[0] : 0;
+    if (examined) *examined = c->grid.frames_ok ? (int64_t)c->frame_stats[1] : 0;
+    return ST_OK;
+}
+
+int st_cert_frames(st_ctx* c, float* frames, uint32_t* margins)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (!c->grid.frames_ok) return fail(c, ST_ESTATE, "st_cert_frames: this grid has no cell frames (coordinates beyond 2^17 km, or SITRACK_B200_NO_CERT/NO_FILTER set)");
+    CU(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)c->Nj * c->Ni;
+    if (frames) CU(c, cudaMemcpy(frames, c->frames, sizeof(float4) * 2 * n, cudaMemcpyDeviceToHost));
+    if (margins) CU(c, cudaMemcpy(margins, c->fmargin, sizeof(unsigned) * n, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_selftest_cert(st_ctx* c, int64_t n, const double* yx, const int32_t* cell, const float* vel4, uint8_t* flags)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (n < 0 || !yx || !cell || !vel4 || !flags) return fail(c, ST_EINVAL, "st_selftest_cert: NULL argument");
+    if (!c->grid.frames_ok) return fail(c, ST_ESTATE, "st_selftest_cert: this grid has no cell frames");
+    if (n == 0) return ST_OK;
+    for (int64_t k = 0; k < n; ++k)
+        if (cell[2 * k] < 1 || cell[2 * k] >= c->Nj || cell[2 * k + 1] < 1 || cell[2 * k + 1] >= c->Ni)
+            return fail(c, ST_EINVAL, "st_selftest_cert: cell outside [1,Nj-1]x[1,Ni-1]");
+    CU(c, cudaSetDevice(c->device));
+    Scratch s; double* dyx; int32_t* dc; float* dv; uint8_t* df;
+    CU(c, s.up(&dyx, yx, (size_t)2 * n)); CU(c, s.up(&dc, cell, (size_t)2 * n)); CU(c, s.up(&dv, vel4, (size_t)4 * n));
+    CU(c, s.alloc(&df, (size_t)n));
+    CU(c, launch_cert_selftest(c->grid, n, (const pt*)dyx, (const int2*)dc, (const float4*)dv, df, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(flags, df, (size_t)n, cudaMemcpyDeviceToHost));
     return ST_OK;
 }
 

@@ -13,6 +13,9 @@
 namespace st {
 
 #define ST_FILL (-9999.0)                 // sitrack/ncio.py:19 FillValue
+// A discontinued buoy (iAlive = 0, si3_part_tracker.py:483-484) carries bit 31 in the jT word of its cell as well
+// as alive = 0: the default step kernel streams 24 B of state per buoy (pos, cell) and never touches `alive`.
+#define ST_DEAD_BIT ((int)0x80000000)
 
 // A point of the km plane, stored [y, x] like every coordinate pair upstream.
 struct __align__(16) pt { double y, x; };
@@ -53,6 +56,40 @@ __device__ __forceinline__ void st_stream_pt(pt* a, pt v)
 {
     __stcs(reinterpret_cast<double2*>(a), make_double2(v.y, v.x));
 }
+
+// ---- TMA bulk copies (global -> shared) completing on an mbarrier: the state ring of k_advect_cert ----------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int cnt)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity)
+{
+    const uint32_t a = smem_u32(b);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+// the same with an L2 evict_first hint: the state stream is touch-once
+__device__ __forceinline__ void tma_load_1d_stream(void* dst, const void* src, uint32_t bytes, unsigned long long* b)
+{
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ---- tracking.py:44-49  _ccw_(A,B,C) = (Cy-Ay)*(Bx-Ax) > (By-Ay)*(Cx-Ax) ----
 __device__ __forceinline__ bool ccw(pt A, pt B, pt C)

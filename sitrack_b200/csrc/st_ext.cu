@@ -139,6 +139,7 @@ k_advect_ext(const AdvectGrid g, const float* __restrict__ u, const float* __res
             if (killed(jT, iT, g.Nj, Ni, g.tmask, ic, g.rmin_conc)) { a2 = 0; break; }
         }
         st_stream_pt(s.pos + p, Pn);
+        if (!a2) jT |= ST_DEAD_BIT;
         if (jT != c.x || iT != c.y) s.cell[p] = make_int2(jT, iT);
         if (!a2) s.alive[p] = 0;
     } else if (WIN && prestart) {

@@ -20,6 +20,10 @@ struct AdvectGrid {
                                 //  -- the buoy-independent orientation of the two U/V-pick segment tests (k_cell_bits);
                                 //  bit 2 = the cell is a convex anticlockwise quadrangle with edges shorter than 1024 km
     int filter_ok;              // the grid qualifies for the orientation filter of k_advect_warp (st_create checks)
+    // certified fast path (st_cert.cuh, k_cell_frames): per host cell an affine frame as 8 f32 and two bf16 margins
+    const float4* frames;       // (2*Nj*Ni) {oy, ox, a, b}, {c, d, es, et}
+    const unsigned* fmargin;    // (Nj*Ni) bf16(hin) << 16 | bf16(msep); hin = -1: nothing is certified in this cell
+    int frames_ok;              // frames were built (filter_ok and the build succeeded)
     ProjConst proj;
     const AngEntry* atab;       // 47-entry angle table of inv_stere_fast (device)
 };
@@ -80,6 +84,9 @@ cudaError_t launch_advect_ext(const AdvectGrid& g, const float* u, const float* 
                               const BuoyState& s, int jrec, const StepOut& o, int scheme, int interp, int max_hops,
                               cudaStream_t st);
 cudaError_t launch_cell_bits(const AdvectGrid& g, int8_t* bits, int* n_bad_coord, cudaStream_t st);
+cudaError_t launch_cell_frames(const AdvectGrid& g, float4* frames, unsigned* fmargin, unsigned long long* stats, cudaStream_t st);
+cudaError_t launch_cert_selftest(const AdvectGrid& g, long long n, const pt* yx, const int2* cell, const float4* vel,
+                                 uint8_t* flags, cudaStream_t st);
 cudaError_t launch_divcore(const double* a, const double* b, double* q_fast, double* q_div, long long n, cudaStream_t st);
 cudaError_t launch_div1000(const double* a, double* q_fast, double* q_div, long long n, cudaStream_t st);
 cudaError_t launch_advect_multi(const AdvectGrid& g, const float* rec0, long long rec_stride, int nrec,

@@ -50,6 +50,7 @@ k_advect_persist(const AdvectGrid g, const float* __restrict__ u, const float* _
             { const double2 q = *reinterpret_cast<const double2*>(&qPn[e]); B.y = q.x; B.x = q.y; }
             walk_cell(g, ic, A, B, cc.x, cc.y, a2);
             const unsigned p = qI[e];
+            if (!a2) cc.x |= ST_DEAD_BIT;
             if (cc.x != j0 || cc.y != i0) __stcs(s.cell + p, cc);
             if (!a2) s.alive[p] = 0;
         }

@@ -37,29 +37,6 @@ struct PipeSmem {
     int nalive;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* b, int cnt)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(cnt) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* b)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity)
-{
-    const uint32_t a = smem_u32(b);
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
-    } while (!done);
-}
 __device__ __forceinline__ void cp_async16(void* dst, const void* src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -110,6 +87,7 @@ __device__ __forceinline__ void pipe_walk(PipeSmem& sm, int tid, int lo, int n, 
         int8_t a2 = 1;
         walk_cell(g, ic, lds_pt(&sm.qP[e]), lds_pt(&sm.qPn[e]), cc.x, cc.y, a2);
         const unsigned p = sm.qI[e];
+        if (!a2) cc.x |= ST_DEAD_BIT;
         if (cc.x != j0 || cc.y != i0) __stcs(s.cell + p, cc);
         if (!a2) s.alive[p] = 0;
     }

@@ -59,6 +59,7 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
             if (out) {
                 walk_cell(g, ic, A, B, cc.x, cc.y, a2);
                 const unsigned p = qI[wid][e];
+                if (!a2) cc.x |= ST_DEAD_BIT;
                 if (cc.x != j0 || cc.y != i0) __stcs(s.cell + p, cc);
                 if (!a2) s.alive[p] = 0;
             }

@@ -104,9 +104,33 @@ class TrackEngine:
         self.close()
 
     def set_kernel_variant(self, variant):
-        """0 = k_advect_warp (default), 1 = k_advect_step_v1 (straightforward A/B reference); the other
-        launch shapes and kernel families are listed in include/sitrack_b200.h."""
+        """0 = k_advect_cert (default), 1 = k_advect_step_v1 (straightforward A/B reference), 2 / 3 =
+        k_advect_warp with / without the orientation filter; see include/sitrack_b200.h."""
         check(self.L.st_set_kernel_variant(self.h, int(variant)), self.h)
+
+    # -- diagnostics of the certified fast path (csrc/st_cert.cuh) ----------------------------
+    def cert_stats(self):
+        """-> (cells admitted to the certified fast path, cells examined)."""
+        a, e = C.c_int64(0), C.c_int64(0)
+        check(self.L.st_cert_stats(self.h, C.byref(a), C.byref(e)), self.h)
+        return a.value, e.value
+
+    def cert_frames(self):
+        """-> frames (Nj,Ni,8) f4 [oy ox a b c d es et], hin (Nj,Ni) f4, msep (Nj,Ni) f4 (hin = -1: never certified)."""
+        fr = np.zeros((self.Nj, self.Ni, 8), np.float32)
+        mw = np.zeros((self.Nj, self.Ni), np.uint32)
+        check(self.L.st_cert_frames(self.h, hptr(fr), hptr(mw)), self.h)
+        hin = (mw & np.uint32(0xffff0000)).view(np.float32)
+        msep = (mw << np.uint32(16)).view(np.float32)
+        return fr, hin, msep
+
+    def selftest_cert(self, yx, cell, vel4):
+        """flags (n,) u8 of st_selftest_cert: bit0 pick certified, bit1 stay certified, bit2/3 certified
+        llum1/llvm1, bit4/5 the reference's, bit6 the reference's inside test of the reference's new position."""
+        yx, cell, vel4 = as_c(yx, np.float64).reshape(-1, 2), as_c(cell, np.int32).reshape(-1, 2), as_c(vel4, np.float32).reshape(-1, 4)
+        fl = np.zeros(yx.shape[0], np.uint8)
+        check(self.L.st_selftest_cert(self.h, yx.shape[0], hptr(yx), hptr(cell), hptr(vel4), hptr(fl)), self.h)
+        return fl
 
     # -- seeding -----------------------------------------------------------------------
     def set_locate_grid(self, latT, lonT, resKM=None):
