@@ -131,14 +131,15 @@ def ncu_traffic(workload):
 # ---------------------------------------------------------------------------------------------
 # workload construction (host numpy; not timed)
 # ---------------------------------------------------------------------------------------------
-def build_workload(name, rank, want_latlon_grid=True, n_dense=None):
+def build_workload(name, rank, want_latlon_grid=True, n_dense=None, keep_cells=False):
     import synth
     w = WORKLOADS[name]
     t0 = time.time()
     g = synth.make_grid(**synth.GRID_PRESETS[w["grid"]], seed=0, with_latlon=want_latlon_grid)
     U, V, IC = synth.make_records(g, w["nrec_res"], seed=1)
     if w["kind"] == "dense":
-        ids, SG, SC = synth.dense_seeds(g, n_dense or w["buoys"], IC[0], seed=3 + rank, with_latlon=False, box=SEED_BOX)
+        ids, SG, SC = synth.dense_seeds(g, n_dense or w["buoys"], IC[0], seed=3 + rank, with_latlon=False, box=SEED_BOX,
+                                        cells_out=g if keep_cells else None)
     elif w["kind"] == "hss5":
         ids, SG, SC = synth.hss_seeds(g, IC[0], khss=5)
     else:
@@ -492,19 +493,36 @@ def nP_max(nP, dist, dev):
 # ---------------------------------------------------------------------------------------------
 # CPU baselines (oracle/ is only ever the thing timed here, never on the product path)
 # ---------------------------------------------------------------------------------------------
+class _PyShard:
+    """One shard of buoys advanced by the reference's interpreted loop (oracle/pyport.py), one record per call,
+    followed like upstream by the conversion of the whole new row to lat/lon (si3_part_tracker.py:493; the
+    reference calls PROJ, compiled C, through cartopy -- here the oracle's C restatement of it)."""
+
+    def __init__(self, g, recs64, pos, cell):
+        nP = pos.shape[0]
+        self.g, self.recs64 = g, recs64
+        self.cur = pos.copy(); self.nxt = np.empty_like(self.cur); self.m = np.zeros(nP, 'i1')
+        self.jiT = cell.astype(int).copy(); self.alive = np.ones(nP, 'i1')
+        self.first = np.zeros(nP, int); self.last = np.zeros(nP, int) + 10 ** 9
+        self.vM = np.zeros((nP, 4, 2)); self.sin_ = np.zeros(nP, bool)
+
+    def record(self, k):
+        from oracle import pyport, corc
+        xU, xV, xIC = self.recs64[k % len(self.recs64)]
+        self.nxt[:] = pyport.FILL                                   # :327, rows of discontinued buoys stay at the fill value
+        n = pyport.advance(self.g, xU, xV, xIC, k, self.cur, self.nxt, self.m, self.jiT, self.alive, self.first,
+                           self.last, self.vM, self.sin_)
+        corc.inv_stere(self.nxt)                                    # :493, every row, dead ones included
+        self.cur, self.nxt = self.nxt, self.cur
+        return n
+
+
 def _py_sample_run(g, recs64, pos, cell, nrec):
-    from oracle import pyport
-    nP = pos.shape[0]
-    cur = pos.copy(); nxt = np.empty_like(cur); m = np.zeros(nP, 'i1')
-    jiT = cell.astype(int).copy(); alive = np.ones(nP, 'i1')
-    first = np.zeros(nP, int); last = np.zeros(nP, int) + 10 ** 9
-    vM = np.zeros((nP, 4, 2)); sin_ = np.zeros(nP, bool)
+    sh = _PyShard(g, recs64, pos, cell)
     n = 0
     t0 = time.perf_counter()
     for k in range(nrec):
-        xU, xV, xIC = recs64[k % len(recs64)]
-        n += pyport.advance(g, xU, xV, xIC, k, cur, nxt, m, jiT, alive, first, last, vM, sin_)
-        cur, nxt = nxt, cur
+        n += sh.record(k)
     return n, time.perf_counter() - t0
 
 
@@ -520,8 +538,8 @@ def cpu_baseline(g, recs, pos0, cell0, args):
     recs64 = [(U[k].astype(np.float64), V[k].astype(np.float64), IC[k].astype(np.float64)) for k in range(U.shape[0])]
     n, dt = _py_sample_run(g, recs64, pos0[sel], cell0[sel], args.cpu_records)
     out = {"value": n / dt, "unit": "buoy-steps/s", "cores": 1, "kind": "port",
-           "sample": "oracle/pyport.py (interpreted Python like the reference) on %d random buoys of the workload x %d "
-                     "records, %.1f s" % (npy, args.cpu_records, dt)}
+           "sample": "oracle/pyport.py (interpreted Python like the reference, lat/lon conversion of every row included) "
+                     "on %d random buoys of the workload x %d records, %.1f s" % (npy, args.cpu_records, dt)}
     nc = min(nP, 200_000)
     selc = np.sort(rng.choice(nP, nc, replace=False))
     nrc = 24
@@ -536,89 +554,84 @@ def cpu_baseline(g, recs, pos0, cell0, args):
     return out
 
 
-def _ref_worker(conn, g, recs64, pos, cell):
-    from oracle import pyport
-    nP = pos.shape[0]
-    cur = pos.copy(); nxt = np.empty_like(cur); m = np.zeros(nP, 'i1')
-    jiT = cell.astype(int).copy(); alive = np.ones(nP, 'i1')
-    first = np.zeros(nP, int); last = np.zeros(nP, int) + 10 ** 9
-    vM = np.zeros((nP, 4, 2)); sin_ = np.zeros(nP, bool)
-    while True:
-        k = conn.recv()
-        if k is None:
-            break
-        xU, xV, xIC = recs64[k % len(recs64)]
-        n = pyport.advance(g, xU, xV, xIC, k, cur, nxt, m, jiT, alive, first, last, vM, sin_)
-        cur, nxt = nxt, cur
-        conn.send(n)
+def _ref_worker(conn, barrier, g, recs64, pos, cell, W, K):
+    """W warm-up records, a barrier, then K timed records without talking to the parent; reports once."""
+    sh = _PyShard(g, recs64, pos, cell)
+    for k in range(W):
+        sh.record(k)
+    barrier.wait()
+    t0 = time.perf_counter()                                       # CLOCK_MONOTONIC: comparable across processes
+    n = 0
+    for k in range(W, W + K):
+        n += sh.record(k)
+    conn.send((n, t0, time.perf_counter()))
 
 
 def run_reference(args):
     """The reference's CPU implementation of the path (interpreted Python; oracle/pyport.py is its
     pinned port because /root/reference cannot travel to the GPU box) on all host cores: buoys are
-    independent, so each worker process owns a shard of a bounded sample of the same workload."""
+    independent, so each worker process owns a shard of a bounded sample of the same workload and runs the
+    whole W + K record loop on its own (one message back at the end).  The sample is sized for at least
+    ~2 s of timed work per worker: max(--ref-buoys-per-core, 140000 / K) buoys each."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     K, W = args.steps, args.warmup
     wl = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    per = args.ref_buoys_per_core
-    g, (U, V, IC), SG, SC = build_workload(args.workload, 0, want_latlon_grid=(wl["kind"] != "dense"),
-                                           n_dense=4 * cores * per)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per = max(args.ref_buoys_per_core, -(-140000 // max(K, 1)))
+    dense = wl["kind"] == "dense"
+    g, (U, V, IC), SG, SC = build_workload(args.workload, 0, want_latlon_grid=not dense,
+                                           n_dense=cores * per if dense else None, keep_cells=True)
     g.pop("warp", None)
     from oracle import corc
-    # host cells of the sample: nearest T-point in the km plane, then the oracle's containing-cell search
-    n = min(SC.shape[0], cores * per)
     rng = np.random.default_rng(7)
-    sel = np.sort(rng.choice(SC.shape[0], n, replace=False))
-    pos = SC[sel]
-    cell = np.zeros((n, 2), np.int64)
+    if dense:
+        # the synthetic cloud is generated cell by cell: the cell of origin is the host cell; the oracle's
+        # inside test confirms it buoy by buoy
+        pos, cell = SC, g.pop("seed_cells").astype(np.int64)
+    else:
+        n = SC.shape[0]
+        cell = np.zeros((n, 2), np.int64)
+        for b in range(n):
+            cell[b] = _guess_cell(g, SC[b])
+        pos = SC
+    n = pos.shape[0]
     ok = np.zeros(n, bool)
-    Yt, Xt = g["Yt"], g["Xt"]
-    for b in range(n):                                             # nearest T in the km plane, then the 5-candidate test
-        d2 = (Yt - pos[b, 0]) ** 2 + (Xt - pos[b, 1]) ** 2 if n <= 4096 and Yt.size <= 400_000 else None
-        if d2 is not None:
-            j, i = np.unravel_index(np.argmin(d2), Yt.shape)
-        else:
-            j, i = _guess_cell(g, pos[b])
+    for b in range(n):
+        j, i = int(cell[b, 0]), int(cell[b, 1])
         if 2 <= j <= g["Nj"] - 3 and 2 <= i <= g["Ni"] - 3:
             ok[b], cell[b, 0], cell[b, 1] = corc.find_containing_cell(pos[b, 0], pos[b, 1], j, i, g["Yf"], g["Xf"])
     pos, cell = pos[ok], cell[ok]
     n = pos.shape[0]
     recs64 = [(U[k].astype(np.float64), V[k].astype(np.float64), IC[k].astype(np.float64)) for k in range(U.shape[0])]
     ctx = mp.get_context("fork")
-    shards = np.array_split(np.arange(n), cores)
+    barrier = ctx.Barrier(cores)
+    perm = rng.permutation(n)                                     # every worker gets a spatially mixed shard
+    shards = np.array_split(perm, cores)
     procs, conns = [], []
-    for s in shards:
+    for sh in shards:
         a, b = ctx.Pipe()
-        p = ctx.Process(target=_ref_worker, args=(b, g, recs64, pos[s], cell[s]), daemon=True)
+        p = ctx.Process(target=_ref_worker, args=(b, barrier, g, recs64, pos[sh], cell[sh], W, K), daemon=True)
         p.start(); procs.append(p); conns.append(a)
-
-    def step(k):
-        for c in conns:
-            c.send(k)
-        return sum(c.recv() for c in conns)
-    for k in range(W):
-        step(k)
-    t0 = time.perf_counter()
-    done = 0
-    for k in range(W, W + K):
-        done += step(k)
-    dt = time.perf_counter() - t0
-    for c in conns:
-        c.send(None)
+    res = [c.recv() for c in conns]
     for p in procs:
-        p.join(timeout=5)
+        p.join(timeout=10)
+    done = sum(r[0] for r in res)
+    dt = max(r[2] for r in res) - min(r[1] for r in res)
     value = done / dt
-    sample = ("oracle/pyport.py (pinned port of the reference's interpreted loop) on %d host processes, "
-              "%d buoys of the workload per step (bounded sample), %d steps in %.1f s" % (cores, n, K, dt))
+    per_core = [r[0] / (r[2] - r[1]) for r in res]
+    sample = ("oracle/pyport.py (pinned port of the reference's interpreted loop, lat/lon conversion of every row "
+              "included) on %d host processes, %d buoys of the workload (bounded sample, %d per process), %d records "
+              "in %.1f s; %.0f buoy-steps/s per process (min %.0f, max %.0f)"
+              % (cores, n, n // cores, K, dt, value / cores, min(per_core), max(per_core)))
     out = {"impl": "reference", "metric": "buoy-steps/sec", "value": value, "unit": "buoy-steps/s",
            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": round(dt / K * 1e3, 4),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": wl["label"], "grid": [g["Nj"], g["Ni"]], "sample_buoys": n},
-           "cpu_baseline": {"value": value, "unit": "buoy-steps/s", "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": value, "unit": "buoy-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                            "per_core": value / cores},
            "e2e": {"value": value, "unit": "buoy-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)
@@ -653,7 +666,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2000, help="buoys in the Python cpu_baseline sample")
     ap.add_argument("--cpu-records", type=int, default=100)
-    ap.add_argument("--ref-buoys-per-core", type=int, default=96)
+    ap.add_argument("--ref-buoys-per-core", type=int, default=2000)
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 100 if args.steps is None else args.steps

@@ -56,13 +56,15 @@ int  st_create(st_ctx **out, int device, int Nj, int Ni,
 void st_destroy(st_ctx *ctx);
 
 /* Step-kernel variant, all bit-identical in their results:
- *   0 (default) k_advect_cert: persistent one-warp CTAs; U/V pick and inside test decided from a 36-byte
- *     per-cell frame in f32 when provably equal to the reference's tests, the reference's own tests in dense
- *     passes over queued buoys otherwise (csrc/st_cert.cuh);
+ *   0 = 2 (default) k_advect_warp: persistent one-warp CTAs, every warp owns its tiles of 32 buoys and its own
+ *     shared-memory queue of cell crossings; orientation filter for the inside test; 3 the same with the
+ *     reference's inside test on every lane;
  *   1 k_advect_step_v1, the straightforward kernel (also SITRACK_B200_KERNEL=v1);
- *   2 k_advect_warp (round-1 default: full f8 geometry gathers, orientation filter for the inside test), 3 the
- *     same with the reference's inside test on every lane;
- *   4, 6-11 round-1 experiments, present only in -DST_EXPERIMENTS builds (ST_EINVAL otherwise).             */
+ *   4 k_advect_cert + k_walk, the certified two-kernel step: U/V pick and inside test decided from a 32-byte
+ *     per-cell frame in f32 when provably equal to the reference's tests, the reference's own tests in a second
+ *     dense kernel otherwise (csrc/st_cert.cuh; builds the frames on first use; measured slower than 0 on B200
+ *     because the second kernel re-reads what the first had in registers -- kept as an A/B);
+ *   6-12 round-1 experiments, present only in -DST_EXPERIMENTS builds (ST_EINVAL otherwise).                  */
 int  st_set_kernel_variant(st_ctx *ctx, int variant);
 
 /* Polar-stereographic parameters of CartNPSkm2Geo1D (util.py:413: lat0=70, lon0=-45). */
@@ -250,18 +252,25 @@ int  st_selftest_xy2latlon_fast(int device, int64_t n, const double *yx, double 
 /* Diagnostics: the step kernel divides displacements by 1000 (si3_part_tracker.py:457-458)
  * with a reciprocal + exact-residual sequence; q_fast is that result, q_div the IEEE
  * division, for n host values a.                                                          */
+/* The three projection kernels on an arbitrary ellipsoid (semi-major axis a_m [m], flattening f), so that they can be
+ * pinned to published values that are not on WGS84 (tests/golden/proj_kat.json: Snyder 1987's worked example on
+ * Clarke 1866, NSIDC's grid-corner table on Hughes 1980).  which = 0: inv_stere (st_xy2latlon), 1: inv_stere_fast
+ * (the step kernel's), 2: fwd_stere (st_latlon2xy).  in/out are (n,2): [y,x] km <-> [lat,lon] degrees.            */
+int  st_selftest_proj(int device, int which, int64_t n, const double *in, double *out, double lat_ts, double lon0,
+                      double a_m, double f);
+
 int  st_selftest_div1000(int device, int64_t n, const double *a, double *q_fast, double *q_div);
 /* Same for the branch-free general division of the inside test (locate.py:72): q_fast = the
  * kernel's nine-operation sequence, q_div = IEEE division, for n host pairs a/b.            */
 int  st_selftest_divide(int device, int64_t n, const double *a, const double *b, double *q_fast, double *q_div);
 
-/* Diagnostics of the certified fast path of the default step kernel (csrc/st_cert.cuh).  The kernel decides the
+/* Diagnostics of the certified fast path of step variant 4 (csrc/st_cert.cuh).  The kernel decides the
  * U/V pick (si3_part_tracker.py:430-441) and "still inside its cell" (locate.py:49-78) from a per-cell affine
  * frame in f32 whenever the buoy is farther than proven margins from every line involved, and runs the
  * reference's own tests otherwise.
  *   st_cert_stats     cells admitted to the fast path / cells examined (0/0 when the grid has no frames).
- *   st_cert_frames    host copies of the frames ((Nj,Ni,8) f32: oy ox a b c d es et) and of the packed margins
- *                     ((Nj,Ni) u32: bf16(hin) << 16 | bf16(msep)); either may be NULL.
+ *   st_cert_frames    host copies of the frames ((Nj,Ni,8) f32: oy ox a b c d es et, es/et expanded from their bf16
+ *                     storage) and of the packed margins ((Nj,Ni) u32: bf16(hin) << 16 | bf16(msep)); either may be NULL.
  *   st_selftest_cert  for n host triples (position yx (n,2), host cell (n,2), face velocities vel4 (n,4) f4 =
  *                     uL uR vB vT) returns flags (n) u8: bit0 pick certified, bit1 stay certified, bit2/bit3 the
  *                     certified llum1/llvm1, bit4/bit5 the reference's llum1/llvm1, bit6 the reference's

@@ -49,6 +49,10 @@ def lib():
         L.orc_inv_stere.restype = None
         L.orc_fwd_stere.argtypes = [C.c_long, _f8, _f8, C.c_double, C.c_double]
         L.orc_fwd_stere.restype = None
+        L.orc_inv_stere_ell.argtypes = [C.c_long, _f8, _f8, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.orc_inv_stere_ell.restype = None
+        L.orc_fwd_stere_ell.argtypes = [C.c_long, _f8, _f8, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.orc_fwd_stere_ell.restype = None
         L.orc_haversine.argtypes = [C.c_double] * 4
         L.orc_haversine.restype = C.c_double
         L.orc_nearest_point.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, _f8, _f8, C.c_void_p,
@@ -98,17 +102,27 @@ def new_host_cell(kcross, p1, p2, jT, iT, Yf, Xf):
                                      _c(Yf, "f8"), _c(Xf, "f8"), Yf.shape[1])
 
 
-def inv_stere(yx, lat_ts=70.0, lon0=-45.0):
+WGS84 = (6378137.0, 1.0 / 298.257223563)
+
+
+def inv_stere(yx, lat_ts=70.0, lon0=-45.0, ellipsoid=None):
+    """[y,x] km -> [lat,lon] degrees; ellipsoid = (a [m], f), default WGS84 (the reference's case)."""
     yx = _c(yx, "f8").reshape(-1, 2)
     out = np.empty_like(yx)
-    lib().orc_inv_stere(yx.shape[0], yx, out, lat_ts, lon0)
+    if ellipsoid is None:
+        lib().orc_inv_stere(yx.shape[0], yx, out, lat_ts, lon0)
+    else:
+        lib().orc_inv_stere_ell(yx.shape[0], yx, out, lat_ts, lon0, float(ellipsoid[0]), float(ellipsoid[1]))
     return out
 
 
-def fwd_stere(latlon, lat_ts=70.0, lon0=-45.0):
+def fwd_stere(latlon, lat_ts=70.0, lon0=-45.0, ellipsoid=None):
     ll = _c(latlon, "f8").reshape(-1, 2)
     out = np.empty_like(ll)
-    lib().orc_fwd_stere(ll.shape[0], ll, out, lat_ts, lon0)
+    if ellipsoid is None:
+        lib().orc_fwd_stere(ll.shape[0], ll, out, lat_ts, lon0)
+    else:
+        lib().orc_fwd_stere_ell(ll.shape[0], ll, out, lat_ts, lon0, float(ellipsoid[0]), float(ellipsoid[1]))
     return out
 
 

@@ -218,14 +218,14 @@ static double adjlon(double lam)
     return lam - PI_;
 }
 
-/* km (y,x) -> degrees (lat,lon), n points, yx and latlon are (n,2). */
-void orc_inv_stere(long n, const double *yx, double *latlon, double lat_ts, double lon0)
+/* km (y,x) -> degrees (lat,lon), n points, yx and latlon are (n,2), on the ellipsoid (a [m], f). */
+void orc_inv_stere_ell(long n, const double *yx, double *latlon, double lat_ts, double lon0, double a_m, double f)
 {
-    const double es = WGS84_F * (2.0 - WGS84_F), e = sqrt(es);
+    const double es = f * (2.0 - f), e = sqrt(es);
     const double akm1 = stere_akm1(lat_ts, e);
     for (long k = 0; k < n; ++k) {
-        double x = (1000.0 * yx[2 * k + 1]) / WGS84_A;
-        double y = (1000.0 * yx[2 * k + 0]) / WGS84_A;
+        double x = (1000.0 * yx[2 * k + 1]) / a_m;
+        double y = (1000.0 * yx[2 * k + 0]) / a_m;
         double rho = hypot(x, y);
         y = -y;                                       /* N_POLE */
         double tp = -rho / akm1;
@@ -244,10 +244,16 @@ void orc_inv_stere(long n, const double *yx, double *latlon, double lat_ts, doub
     }
 }
 
-/* degrees (lat,lon) -> km (y,x) ; sitrack/util.py:394-410,434-451 */
-void orc_fwd_stere(long n, const double *latlon, double *yx, double lat_ts, double lon0)
+/* the reference's case: WGS84, the globe cartopy gives NorthPolarStereo by default */
+void orc_inv_stere(long n, const double *yx, double *latlon, double lat_ts, double lon0)
 {
-    const double es = WGS84_F * (2.0 - WGS84_F), e = sqrt(es);
+    orc_inv_stere_ell(n, yx, latlon, lat_ts, lon0, WGS84_A, WGS84_F);
+}
+
+/* degrees (lat,lon) -> km (y,x) ; sitrack/util.py:394-410,434-451 */
+void orc_fwd_stere_ell(long n, const double *latlon, double *yx, double lat_ts, double lon0, double a_m, double f)
+{
+    const double es = f * (2.0 - f), e = sqrt(es);
     const double akm1 = stere_akm1(lat_ts, e);
     for (long k = 0; k < n; ++k) {
         double phi = latlon[2 * k + 0] * DEG2RAD;
@@ -256,9 +262,13 @@ void orc_fwd_stere(long n, const double *latlon, double *yx, double lat_ts, doub
         double x = (fabs(phi - HALFPI) < 1e-15) ? 0.0 : akm1 * tsfn(phi, sinphi, e);
         double y = -x * cos(lam);                     /* N_POLE: y = -rho*cos(lam) */
         x = x * sin(lam);
-        yx[2 * k + 0] = WGS84_A * y / 1000.0;
-        yx[2 * k + 1] = WGS84_A * x / 1000.0;
+        yx[2 * k + 0] = a_m * y / 1000.0;
+        yx[2 * k + 1] = a_m * x / 1000.0;
     }
+}
+void orc_fwd_stere(long n, const double *latlon, double *yx, double lat_ts, double lon0)
+{
+    orc_fwd_stere_ell(n, latlon, yx, lat_ts, lon0, WGS84_A, WGS84_F);
 }
 
 /* ======================================================================= *

@@ -31,6 +31,7 @@ SIGNATURES = {
     "st_set_projection": (c_int, [vp, c_dbl, c_dbl]),
     "st_set_kernel_variant": (c_int, [vp, c_int]),
     "st_selftest_xy2latlon_fast": (c_int, [c_int, c_i64, vp, vp, c_dbl, c_dbl]),
+    "st_selftest_proj": (c_int, [c_int, c_int, c_i64, vp, vp, c_dbl, c_dbl, c_dbl, c_dbl]),
     "st_selftest_div1000": (c_int, [c_int, c_i64, vp, vp, vp]),
     "st_selftest_divide": (c_int, [c_int, c_i64, vp, vp, vp, vp]),
     "st_cert_stats": (c_int, [vp, C.POINTER(c_i64), C.POINTER(c_i64)]),

@@ -27,7 +27,7 @@ struct st_ctx {
     pt *F = nullptr, *U = nullptr, *V = nullptr;
     int8_t* tmask = nullptr;
     int8_t* cellbits = nullptr;
-    float4* frames = nullptr; unsigned* fmargin = nullptr;      // certified fast path (k_cell_frames)
+    float4* frames = nullptr;                                   // certified fast path (k_cell_frames)
     unsigned long long frame_stats[2] = {0, 0};                 // cells admitted / examined
     double *latT = nullptr, *lonT = nullptr, *resKM = nullptr;
     int *bin_start = nullptr, *bin_pts = nullptr;
@@ -37,6 +37,7 @@ struct st_ctx {
     // buoys
     long long nP = 0, capP = 0;
     pt* pos = nullptr; int2* cell = nullptr; int8_t* alive = nullptr;
+    WalkScratch wq = {nullptr, nullptr, nullptr, nullptr};               // scratch between k_advect_cert and k_walk
     unsigned long long* n_bad_cell = nullptr;                   // buoys st_set_buoys discontinued for an out-of-range cell
     int32_t *rec_first = nullptr, *rec_last = nullptr;
     bool has_window = false;
@@ -124,7 +125,7 @@ static void fit_lat_poly(double e_, double out[ST_LAT_DEG + 1])
     for (int k = 0; k < N; ++k) out[k] = (double)a[k];
 }
 
-static ProjConst make_proj(double lat_ts, double lon0)
+static ProjConst make_proj(double lat_ts, double lon0, double kA = ::kA, double kF = ::kF)
 {
     const double es = kF * (2.0 - kF), e = sqrt(es);
     const double n = kF / (2.0 - kF), n2 = n * n, n3 = n2 * n, n4 = n3 * n, n5 = n4 * n, n6 = n5 * n;
@@ -153,7 +154,7 @@ static ProjConst make_proj(double lat_ts, double lon0)
     p.wrap_up = lon0 > 0.0;
     return p;
 }
-static ProjFwdConst make_proj_fwd(double lat_ts, double lon0)
+static ProjFwdConst make_proj_fwd(double lat_ts, double lon0, double kA = ::kA, double kF = ::kF)
 {
     const double es = kF * (2.0 - kF), e = sqrt(es);
     ProjFwdConst p;
@@ -286,34 +287,55 @@ int st_create(st_ctx** out, int device, int Nj, int Ni, const double* Yf, const 
         // the orientation filter's error bound assumes km coordinates within 2^17 (inside_margin)
         c->grid.filter_ok = (bad == 0) && !getenv("SITRACK_B200_NO_FILTER");
     }
-    // frames and margins of the certified fast path (k_advect_cert); SITRACK_B200_NO_CERT=1 keeps the round-1 default
-    if (e == cudaSuccess && c->grid.filter_ok && !getenv("SITRACK_B200_NO_CERT")) {
-        unsigned long long* d_stats = nullptr;
-        e = cudaMalloc(&c->frames, sizeof(float4) * 2 * n);
-        if (e == cudaSuccess) e = cudaMalloc(&c->fmargin, sizeof(unsigned) * n);
-        if (e == cudaSuccess) e = cudaMalloc(&d_stats, 2 * sizeof(unsigned long long));
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), c->stream);
-        if (e == cudaSuccess) e = launch_cell_frames(c->grid, c->frames, c->fmargin, d_stats, c->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(c->frame_stats, d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        cudaFree(d_stats);
-        c->grid.frames = c->frames; c->grid.fmargin = c->fmargin;
-        c->grid.frames_ok = (e == cudaSuccess);
-    }
     if (e != cudaSuccess) { rc = cuda_fail(nullptr, e, "st_create(projection tables, cell bits)"); st_destroy(c); return rc; }
     { const char* ev = getenv("SITRACK_B200_KERNEL"); if (ev && ev[0] == 'v' && ev[1] == '1') c->variant = 1; }
     *out = c;
     return ST_OK;
 }
 
+// Frames and margins of the certified two-kernel step (variant 4, csrc/st_cert.cuh), built on first use: 32 B per cell.
+static int ensure_frames(st_ctx* c)
+{
+    if (c->grid.frames_ok) return ST_OK;
+    if (!c->grid.filter_ok) return fail(c, ST_ESTATE, "this grid has no cell frames (coordinates beyond 2^17 km, or SITRACK_B200_NO_FILTER set)");
+    CU(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)c->Nj * c->Ni;
+    unsigned long long* d_stats = nullptr;
+    cudaError_t e = cudaMalloc(&c->frames, sizeof(float4) * 2 * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_stats, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), c->stream);
+    if (e == cudaSuccess) e = launch_cell_frames(c->grid, c->frames, d_stats, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->frame_stats, d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_stats);
+    if (e != cudaSuccess) { cudaFree(c->frames); c->frames = nullptr; return cuda_fail(c, e, "cell frames"); }
+    c->grid.frames = c->frames;
+    c->grid.frames_ok = 1;
+    return ST_OK;
+}
+
+// scratch between k_advect_cert and k_walk, sized like the buoy arrays
+static int ensure_walk_scratch(st_ctx* c)
+{
+    if (c->wq.P || c->capP == 0) return ST_OK;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMalloc(&c->wq.P, sizeof(pt) * c->capP));
+    CU(c, cudaMalloc(&c->wq.maskW, sizeof(unsigned) * (c->capP / 32)));
+    CU(c, cudaMalloc(&c->wq.maskX, sizeof(unsigned) * (c->capP / 32)));
+    CU(c, cudaMalloc(&c->wq.maskA, sizeof(unsigned) * (c->capP / 32)));
+    return ST_OK;
+}
+
 int st_set_kernel_variant(st_ctx* c, int variant)
 {
 #ifdef ST_EXPERIMENTS
-    const bool known = variant >= 0 && variant <= 11 && variant != 5;
+    const bool known = variant >= 0 && variant <= 12 && variant != 5;
 #else
-    const bool known = variant >= 0 && variant <= 3;
+    const bool known = variant >= 0 && variant <= 4;
 #endif
-    if (!c || !known) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 certified fast path (default), 1 v1, 2 warp-private with orientation filter, 3 warp-private exact; 4, 6-11 only in -DST_EXPERIMENTS builds");
+    if (!c || !known) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 = 2 warp-private with orientation filter (default), 1 v1, 3 warp-private exact, 4 certified two-kernel step; 6-12 only in -DST_EXPERIMENTS builds");
+    // a grid that does not qualify for frames (st_create: filter_ok) runs variant 4 as variant 2
+    if (variant == 4 && c->grid.filter_ok) { int rc = ensure_frames(c); if (rc) return rc; }
     c->variant = variant;
     return ST_OK;
 }
@@ -322,9 +344,10 @@ void st_destroy(st_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->F); cudaFree(c->U); cudaFree(c->V); cudaFree(c->tmask); cudaFree(c->atab); cudaFree(c->cellbits); cudaFree(c->frames); cudaFree(c->fmargin);
+    cudaFree(c->F); cudaFree(c->U); cudaFree(c->V); cudaFree(c->tmask); cudaFree(c->atab); cudaFree(c->cellbits); cudaFree(c->frames);
     cudaFree(c->latT); cudaFree(c->lonT); cudaFree(c->resKM); cudaFree(c->bin_start); cudaFree(c->bin_pts);
     cudaFree(c->pos); cudaFree(c->cell); cudaFree(c->alive); cudaFree(c->rec_first); cudaFree(c->rec_last); cudaFree(c->n_bad_cell);
+    cudaFree(c->wq.P); cudaFree(c->wq.maskW); cudaFree(c->wq.maskX); cudaFree(c->wq.maskA);
     cudaFree(c->o_yx); cudaFree(c->o_ll); cudaFree(c->o_mask); cudaFree(c->o_nalive);
     for (float* p : c->d_rec) cudaFree(p);
     for (float* p : c->h_rec) cudaFreeHost(p);
@@ -496,6 +519,8 @@ static int reserve_buoys(st_ctx* c, int64_t nP, bool window, cudaStream_t s)
 {
     if (nP > c->capP) {
         cudaFree(c->pos); cudaFree(c->cell); cudaFree(c->alive); cudaFree(c->rec_first); cudaFree(c->rec_last);
+        cudaFree(c->wq.P); cudaFree(c->wq.maskW); cudaFree(c->wq.maskX); cudaFree(c->wq.maskA);
+        c->wq = WalkScratch{nullptr, nullptr, nullptr, nullptr};
         c->pos = nullptr; c->cell = nullptr; c->alive = nullptr; c->rec_first = c->rec_last = nullptr; c->capP = 0;
         // capacity padded to whole 256-buoy tiles: k_advect_pipe moves state with fixed-size TMA bulk copies
         const long long cap = ((nP + 255) / 256) * 256;
@@ -643,6 +668,7 @@ static BuoyState state_of(st_ctx* c)
     s.nP = c->nP; s.pos = c->pos; s.cell = c->cell; s.alive = c->alive;
     s.rec_first = c->has_window ? c->rec_first : nullptr;
     s.rec_last = c->has_window ? c->rec_last : nullptr;
+    s.q = c->wq;
     return s;
 }
 
@@ -655,6 +681,7 @@ static int step_impl(st_ctx* c, int slot, int jrec, void* out_yx, void* out_latl
     const float* r = c->d_rec[slot];
     StepOut o{(pt*)out_yx, (pt*)out_latlon, out_mask, (unsigned long long*)n_alive};
     o.f4 = f4;
+    if (c->variant == 4) { int rs = ensure_walk_scratch(c); if (rs) return rs; }
     CU(c, launch_advect_step(c->grid, r, r + npt, r + 2 * npt, state_of(c), jrec, o, c->variant, (cudaStream_t)stream));
     return ST_OK;
 }
@@ -880,6 +907,7 @@ int st_step_gather(st_ctx* c, int slot, int jrec, int buf, uint64_t seq, void* o
     // each rank starts with its right-hand neighbour, so that at any moment the ranks' stores fan out
     // over different destinations instead of all converging on rank 0 first
     for (int k = 1; k < g.world; ++k) o.peer_yx[o.npeer++] = g.peer[(g.rank + k) % g.world] + at;
+    if (c->variant == 4) { int rs = ensure_walk_scratch(c); if (rs) return rs; }
     CU(c, launch_advect_step(c->grid, r, r + npt, r + 2 * npt, state_of(c), jrec, o, c->variant, (cudaStream_t)stream));
     return gather_signal_impl(c, 0, seq, stream);
 }
@@ -953,6 +981,7 @@ static int track_record_host_impl(st_ctx* c, int jrec, const float* u, const flo
               n_alive ? c->o_nalive : nullptr};
     o.f4 = f4;
     const size_t rowb = f4 ? sizeof(float2) : sizeof(pt);
+    if (c->variant == 4) { int rs = ensure_walk_scratch(c); if (rs) return rs; }
     CU(c, launch_advect_step(c->grid, d, d + npt, d + 2 * npt, state_of(c), jrec, o, c->variant, s));
     if (c->nP > 0) {
         if (out_yx) CU(c, cudaMemcpyAsync(out_yx, c->o_yx, rowb * c->nP, cudaMemcpyDeviceToHost, s));
@@ -1025,6 +1054,24 @@ int st_latlon2xy(int device, int64_t n, const double* latlon, double* yx, double
     return ST_OK;
 }
 
+int st_selftest_proj(int device, int which, int64_t n, const double* in, double* out, double lat_ts, double lon0,
+                     double a_m, double f)
+{
+    if (n < 0 || !in || !out) return fail(nullptr, ST_EINVAL, "st_selftest_proj: NULL argument");
+    if (which < 0 || which > 2 || !(a_m > 0.0) || !(f >= 0.0 && f < 0.1)) return fail(nullptr, ST_EINVAL, "st_selftest_proj: which in 0..2, a > 0, 0 <= f < 0.1");
+    int rc = use_device(nullptr, device); if (rc) return rc;
+    if (n == 0) return ST_OK;
+    Scratch s; double *a, *b; AngEntry* tab = nullptr;
+    CUS(s.up(&a, in, (size_t)2 * n)); CUS(s.alloc(&b, (size_t)2 * n));
+    if (which == 0) CUS(launch_xy2latlon((const pt*)a, (pt*)b, n, make_proj(lat_ts, lon0, a_m, f), 0));
+    else if (which == 1) {
+        CUS(make_angle_table(&tab)); s.p.push_back(tab);
+        CUS(launch_xy2latlon_fast((const pt*)a, (pt*)b, n, make_proj(lat_ts, lon0, a_m, f), tab, 0));
+    } else CUS(launch_latlon2xy((const pt*)a, (pt*)b, n, make_proj_fwd(lat_ts, lon0, a_m, f), 0));
+    CUS(cudaMemcpy(out, b, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
 int st_selftest_div1000(int device, int64_t n, const double* a, double* q_fast, double* q_div)
 {
     if (n < 0 || !a || !q_fast || !q_div) return fail(nullptr, ST_EINVAL, "st_selftest_div1000: NULL argument");
@@ -1054,6 +1101,7 @@ int st_selftest_divide(int device, int64_t n, const double* a, const double* b, 
 int st_cert_stats(st_ctx* c, int64_t* admitted, int64_t* examined)
 {
     if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (c->grid.filter_ok) { int rc = ensure_frames(c); if (rc) return rc; }
     if (admitted) *admitted = c->grid.frames_ok ? (int64_t)c->frame_stats[0] : 0;
     if (examined) *examined = c->grid.frames_ok ? (int64_t)c->frame_stats[1] : 0;
     return ST_OK;
@@ -1062,11 +1110,20 @@ int st_cert_stats(st_ctx* c, int64_t* admitted, int64_t* examined)
 int st_cert_frames(st_ctx* c, float* frames, uint32_t* margins)
 {
     if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
-    if (!c->grid.frames_ok) return fail(c, ST_ESTATE, "st_cert_frames: this grid has no cell frames (coordinates beyond 2^17 km, or SITRACK_B200_NO_CERT/NO_FILTER set)");
+    { int rc = ensure_frames(c); if (rc) return rc; }
     CU(c, cudaSetDevice(c->device));
     const size_t n = (size_t)c->Nj * c->Ni;
-    if (frames) CU(c, cudaMemcpy(frames, c->frames, sizeof(float4) * 2 * n, cudaMemcpyDeviceToHost));
-    if (margins) CU(c, cudaMemcpy(margins, c->fmargin, sizeof(unsigned) * n, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> raw(8 * n);
+    CU(c, cudaMemcpy(raw.data(), c->frames, sizeof(float4) * 2 * n, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < n; ++k) {
+        const uint32_t mw = raw[8 * k + 6], ew = raw[8 * k + 7];
+        if (margins) margins[k] = mw;
+        if (frames) {
+            memcpy(frames + 8 * k, &raw[8 * k], 6 * sizeof(float));
+            const uint32_t es = ew & 0xffff0000u, et = ew << 16;
+            memcpy(frames + 8 * k + 6, &es, 4); memcpy(frames + 8 * k + 7, &et, 4);
+        }
+    }
     return ST_OK;
 }
 
@@ -1074,7 +1131,7 @@ int st_selftest_cert(st_ctx* c, int64_t n, const double* yx, const int32_t* cell
 {
     if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
     if (n < 0 || !yx || !cell || !vel4 || !flags) return fail(c, ST_EINVAL, "st_selftest_cert: NULL argument");
-    if (!c->grid.frames_ok) return fail(c, ST_ESTATE, "st_selftest_cert: this grid has no cell frames");
+    { int rc = ensure_frames(c); if (rc) return rc; }
     if (n == 0) return ST_OK;
     for (int64_t k = 0; k < n; ++k)
         if (cell[2 * k] < 1 || cell[2 * k] >= c->Nj || cell[2 * k + 1] < 1 || cell[2 * k + 1] >= c->Ni)

@@ -52,28 +52,22 @@
 
 namespace st {
 
-__device__ __forceinline__ float4 ldg_f4_keep(const float4* a)
-{
-    float4 r;
-    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(a), "l"(l2_keep_policy()));
-    return r;
-}
-
 // the certified part of the step for one lane: frame coordinates, pick, Euler step, stay test
 struct CertLane { bool pick_ok, in_ok, left, below; };
 
 template <int UV>
-__device__ __forceinline__ CertLane cert_eval(const float4 f0, const float4 f1, const unsigned mw, pt P,
+__device__ __forceinline__ CertLane cert_eval(const float4 f0, const float4 f1, pt P,
                                               float uL, float uR, float vB, float vT, double rdt, float kdt,
                                               pt& Pn)
 {
+    // f0 = {oy, ox, a, b}, f1 = {c, d, bf16 hin | bf16 msep, bf16 es | bf16 et}:  s = a dx + b dy + es,  t = c dx + d dy + et
+    const unsigned mw = __float_as_uint(f1.z), ew = __float_as_uint(f1.w);
     const float hin = __uint_as_float(mw & 0xffff0000u), msep = __uint_as_float(mw << 16);
-    // f0 = {oy, ox, a, b}, f1 = {c, d, es, et}:  s = a dx + b dy + es,  t = c dx + d dy + et
+    const float es = __uint_as_float(ew & 0xffff0000u), et = __uint_as_float(ew << 16);
     const float dy = __double2float_rn(__dsub_rn(P.y, (double)f0.x));
     const float dx = __double2float_rn(__dsub_rn(P.x, (double)f0.y));
-    const float s = __fmaf_rn(f0.z, dx, __fmaf_rn(f0.w, dy, f1.z));
-    const float t = __fmaf_rn(f1.x, dx, __fmaf_rn(f1.y, dy, f1.w));
+    const float s = __fmaf_rn(f0.z, dx, __fmaf_rn(f0.w, dy, es));
+    const float t = __fmaf_rn(f1.x, dx, __fmaf_rn(f1.y, dy, et));
     const float as = fabsf(s), at = fabsf(t);
     CertLane r;
     r.left = s < 0.0f; r.below = t < 0.0f;
@@ -99,12 +93,46 @@ __device__ __forceinline__ CertLane cert_eval(const float4 f0, const float4 f1, 
     return r;
 }
 
-// the reference's whole step for one lane, exact tests only (dense X pass)
+// Launch shape and data flow.  The memory-system skeleton of the step (tools/micro/stream_skeleton.cu: the same five
+// streams, no gathers, no arithmetic) runs at 7.1 TB/s as a plain one-thread-per-buoy grid at full occupancy and at
+// 5.1-6.5 TB/s as persistent one-warp CTAs with 16-32 warps per SM: what this access mix needs is bytes in flight,
+// i.e. resident threads.  So the step is two plain kernels:
+//   k_advect_cert  one thread per buoy, nothing but the certified fast path (48 registers, no shared memory): state
+//                  in, frame + four face velocities gathered, pick / Euler step / stay decided, rows and state out.
+//                  A lane it cannot certify is only MARKED: one ballot word per tile of 32 buoys for "stay not
+//                  certified" (W), one for "pick not certified" (X); a W lane's old position goes to a scratch array
+//                  at its own index (its state already holds the new one), an X lane's state is left untouched.
+//   k_walk         one thread per marked lane, dense: a block takes ST_WALK_TILES tiles, scans their ballot words and
+//                  deals the marked lanes out to its threads.  W: the reference's inside test on the new position and,
+//                  when outside, CrossedEdge / NewHostCell / UpdtInd4NewCell / Survive.  X: the reference's whole
+//                  step (exact_lane).
+// `alive` is bit 31 of the cell's jT word.
+constexpr int ST_CERT_BLOCK = 256;
+#ifndef ST_CERT_MINBLK
+#define ST_CERT_MINBLK 6                                          // 1536 resident threads per SM at <= 42 registers
+#endif
+#ifndef ST_WALK_TILES
+#define ST_WALK_TILES 24
+#endif
+constexpr int ST_WALK_BLOCK = 128;
+
+__device__ __forceinline__ float4 ldg_f4_keep(const float4* a)
+{
+    float4 r;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(a), "l"(l2_keep_policy()));
+    return r;
+}
+
+// X lanes of k_walk: the reference's whole step with its own tests.  k_advect_cert has already stored a TENTATIVE new
+// position, rows included, from the frame's uncertified pick (whole sectors, like every other lane); it is replaced
+// only when the reference's pick gives a different one -- a lone 16-byte store is expensive (see k_advect_cert).
 template <int UV, int ROWS>
 __device__ __forceinline__ void exact_lane(const AdvectGrid& g, const float* __restrict__ u, const float* __restrict__ v,
-                                           const float* __restrict__ ic, const BuoyState& s, const StepOut& o, unsigned p)
+                                           const float* __restrict__ ic, const BuoyState& s, const StepOut& o,
+                                           const WalkScratch& q, unsigned p)
 {
-    const pt P = ld_stream_pt(s.pos + p);
+    const pt P = ld_stream_pt(q.P + p), Pt = ld_stream_pt(s.pos + p);
     int2 cc = __ldcs(s.cell + p);
     const int j0 = cc.x, i0 = cc.y;
     const int Ni = g.Ni;
@@ -112,28 +140,24 @@ __device__ __forceinline__ void exact_lane(const AdvectGrid& g, const float* __r
     ST_CHECK_CELL(c, Ni + 1, g.Nj, Ni);
     const pt bl = ldg_pt(g.F, c - Ni - 1), br = ldg_pt(g.F, c - Ni);
     const pt ul = ldg_pt(g.F, c - 1),      ur = ldg_pt(g.F, c);
-    double zU, zV;
-    if (UV == 1) {
-        const pt v0 = ldg_pt(g.V, c - Ni), v1 = ldg_pt(g.V, c);
-        const pt u0 = ldg_pt(g.U, c - 1),  u1 = ldg_pt(g.U, c);
-        const float uL = __ldg(u + c - 1), uR = __ldg(u + c);
-        const float vB = __ldg(v + c - Ni), vT = __ldg(v + c);
-        const bool llum1 = intersect2seg(P, ur, v0, v1);           // si3_part_tracker.py:430
-        const bool llvm1 = intersect2seg(P, ur, u0, u1);           // :431
-        zU = (double)(llum1 ? uL : uR);
-        zV = (double)(llvm1 ? vB : vT);
-    } else {
-        zU = __dmul_rn(0.5, __dadd_rn((double)__ldg(u + c), (double)__ldg(u + c - 1)));
-        zV = __dmul_rn(0.5, __dadd_rn((double)__ldg(v + c), (double)__ldg(v + c - Ni)));
-    }
+    const pt v0 = ldg_pt(g.V, c - Ni), v1 = ldg_pt(g.V, c);
+    const pt u0 = ldg_pt(g.U, c - 1),  u1 = ldg_pt(g.U, c);
+    const float uL = __ldg(u + c - 1), uR = __ldg(u + c);
+    const float vB = __ldg(v + c - Ni), vT = __ldg(v + c);
+    const bool llum1 = intersect2seg(P, ur, v0, v1);               // si3_part_tracker.py:430
+    const bool llvm1 = intersect2seg(P, ur, u0, u1);               // :431
+    const double zU = (double)(llum1 ? uL : uR);
+    const double zV = (double)(llvm1 ? vB : vT);
     pt Pn;
     Pn.x = __dadd_rn(P.x, div1000(__dmul_rn(zU, g.rdt)));
     Pn.y = __dadd_rn(P.y, div1000(__dmul_rn(zV, g.rdt)));
-    st_stream_pt(s.pos + p, Pn);
-    if (o.yx) { if (ROWS == 0) st_stream_pt(o.yx + p, Pn); else put_row_yx(o, p, Pn); }
-    if (o.latlon) {
-        const pt ll = inv_stere_fast(Pn, g.proj, g.atab);
-        if (ROWS == 0) st_stream_pt(o.latlon + p, ll); else put_row_pt(o.latlon, p, ll, o.f4);
+    if (__double_as_longlong(Pn.x) != __double_as_longlong(Pt.x) || __double_as_longlong(Pn.y) != __double_as_longlong(Pt.y)) {
+        st_stream_pt(s.pos + p, Pn);
+        if (o.yx) { if (ROWS == 0) st_stream_pt(o.yx + p, Pn); else put_row_yx(o, p, Pn); }
+        if (o.latlon) {
+            const pt ll = inv_stere_fast(Pn, g.proj, g.atab);
+            if (ROWS == 0) st_stream_pt(o.latlon + p, ll); else put_row_pt(o.latlon, p, ll, o.f4);
+        }
     }
     if (!inside_quad_flat(Pn.y, Pn.x, bl, br, ur, ul)) {
         int8_t a2 = 1;
@@ -144,181 +168,133 @@ __device__ __forceinline__ void exact_lane(const AdvectGrid& g, const float* __r
     }
 }
 
-// Launch shape and data flow of k_advect_cert.  Persistent one-warp CTAs (32 per SM); warp w owns tiles
-// w, w + nwarps, ... of 32 buoys.  Per warp, in shared memory:
-//   * a ring of ST_RING state tiles (pos 512 B + cell 256 B each) filled by TMA bulk copies that one lane issues
-//     ST_RING tiles ahead and that complete on a per-stage mbarrier -- the HBM latency of the state stream never
-//     reaches a register scoreboard;
-//   * the W queue (P, Pn, cell, index of lanes whose stay is not certified) and the X queue (index of lanes whose
-//     pick is not certified), both living across tiles and drained 32 entries at a time with every lane busy.
-// The gathers of tile k+1 (36 B of frame + 16 B of velocities per lane, 13 registers) are issued before tile k is
-// computed, so their L2 latency is covered by a whole tile of arithmetic.  `alive` is bit 31 of the cell's jT word.
-#ifndef ST_RING
-#define ST_RING 3
-#endif
-struct CertGather { float4 f0, f1; unsigned mw; float uL, uR, vB, vT; };
-
-template <int UV, bool WIN, int ROWS, int MINB>
-__global__ void __launch_bounds__(32, MINB)
+template <int UV, bool WIN, int ROWS>
+__global__ void __launch_bounds__(ST_CERT_BLOCK, ST_CERT_MINBLK)
 k_advect_cert(const AdvectGrid g, const float* __restrict__ u, const float* __restrict__ v,
-              const float* __restrict__ ic, BuoyState s, int jrec, StepOut o, int ntiles)
+              BuoyState s, int jrec, StepOut o, WalkScratch q)
 {
-    constexpr int QCAP = 64, D = ST_RING;
-    constexpr uint32_t POS_B = 32 * sizeof(pt), CELL_B = 32 * sizeof(int2);
-    __shared__ __align__(128) unsigned char ring[D][POS_B + CELL_B];
-    __shared__ __align__(8) unsigned long long bars[D];
-    __shared__ pt qP[QCAP], qPn[QCAP];
-    __shared__ int2 qC[QCAP];
-    __shared__ unsigned qI[QCAP], qX[QCAP];
-
-    const int lane = threadIdx.x;
-    const unsigned lt = (1u << lane) - 1u;
-    const int nwarps = (int)gridDim.x;
-    const float kdt = __double2float_rn(g.rdt / 1000.0);
+    const long long p = (long long)blockIdx.x * ST_CERT_BLOCK + threadIdx.x;
+    const bool valid = p < s.nP;
     const int Ni = g.Ni;
-
-    auto issue = [&](int tile, int st) {                          // one lane: state tile -> ring stage
-        if (tile < ntiles) {
-            mbar_expect_tx(&bars[st], POS_B + CELL_B);
-            tma_load_1d_stream(ring[st], s.pos + (size_t)tile * 32, POS_B, &bars[st]);
-            tma_load_1d_stream(ring[st] + POS_B, s.cell + (size_t)tile * 32, CELL_B, &bars[st]);
+    pt P = {ST_FILL, ST_FILL};
+    int2 c2 = make_int2(ST_DEAD_BIT | 2, 2);
+    if (valid) { P = ld_stream_pt(s.pos + p); c2 = __ldcs(s.cell + p); }
+    const bool al = c2.x >= 0;
+    bool active = al;
+    bool prestart = false;
+    if (WIN && active) {
+        const int f = s.rec_first[p], l = s.rec_last[p];
+        prestart = (jrec + 1 == f);
+        active = (jrec >= f) && (jrec <= l);
+    }
+    const int c = active ? c2.x * Ni + c2.y : 2 * Ni + 2;
+    ST_CHECK_CELL(c, Ni + 1, g.Nj, Ni);
+    const float4* fr = g.frames + 2 * (size_t)c;
+    const float4 f0 = ldg_f4_keep(fr), f1 = ldg_f4_keep(fr + 1);
+    const float uL = __ldg(u + c - 1), uR = __ldg(u + c);
+    const float vB = __ldg(v + c - Ni), vT = __ldg(v + c);
+    const float kdt = __double2float_rn(g.rdt / 1000.0);
+    pt Pn;
+    const CertLane cl = cert_eval<UV>(f0, f1, P, uL, uR, vB, vT, g.rdt, kdt, Pn);
+    const bool goX = active && !cl.pick_ok;                       // k_walk: Pn is tentative, the reference's own step decides
+    const bool goW = active && cl.pick_ok && !cl.in_ok;           // k_walk: Pn is final; inside test + walk by the reference's tests
+    pt outp = {ST_FILL, ST_FILL};
+    int8_t m = 0;
+    if (active) {
+        outp = Pn; m = 1;
+        st_stream_pt(s.pos + p, outp);
+    } else if (WIN && prestart) {
+        outp = P; m = 1;
+    }
+    // The old position of a marked lane goes to the scratch array in WHOLE 32-byte sectors: a lane and its pair neighbour
+    // both store when either is marked.  A lone 16-byte store leaves a half-written sector behind, and those cost this
+    // step 80 us in k_advect_cert and 95 us in k_walk (read-modify-write at eviction; measured, profiles/README.md).
+    { const int mk = (int)(goW | goX); if (__shfl_xor_sync(0xffffffffu, mk, 1) | mk) { if (valid) q.P[p] = P; } }
+    if (valid) {
+        if (o.mask) __stcs(o.mask + p, m);
+        if (ROWS == 0) { if (o.yx) st_stream_pt(o.yx + p, outp); }
+        else           { if (o.yx) put_row_yx(o, p, outp); }
+        if (o.latlon) {
+            pt ll; ll.y = g.proj.fill_lat; ll.x = g.proj.fill_lon;                    // :493 on a fill row
+            if (m) ll = inv_stere_fast(outp, g.proj, g.atab);
+            if (ROWS == 0) st_stream_pt(o.latlon + p, ll);
+            else           put_row_pt(o.latlon, p, ll, o.f4);
         }
-    };
-    auto gather = [&](int tile, int st) {                         // the frame and the face velocities of the lane's cell
-        const long long p = (long long)tile * 32 + lane;
-        const int2 c2 = *reinterpret_cast<const int2*>(ring[st] + POS_B + lane * sizeof(int2));
-        const bool live = p < s.nP && c2.x >= 0;
-        const int c = live ? c2.x * Ni + c2.y : 2 * Ni + 2;
-        ST_CHECK_CELL(c, Ni + 1, g.Nj, Ni);
-        CertGather r;
-        r.f0 = ldg_f4_keep(g.frames + 2 * (size_t)c); r.f1 = ldg_f4_keep(g.frames + 2 * (size_t)c + 1);
-        r.mw = __ldg(g.fmargin + c);
-        r.uL = __ldg(u + c - 1); r.uR = __ldg(u + c);
-        r.vB = __ldg(v + c - Ni); r.vT = __ldg(v + c);
-        return r;
-    };
-    auto walk_pass = [&](int lo, int n) {                         // dense W pass: pick certified, stay not
-        __syncwarp();
-        if (lane < n) {
-            const int e = lo + lane;
-            int2 cc = qC[e];
+    }
+    const unsigned balW = __ballot_sync(0xffffffffu, goW);
+    const unsigned balX = __ballot_sync(0xffffffffu, goX);
+    const unsigned balA = __ballot_sync(0xffffffffu, valid && al);
+    if ((threadIdx.x & 31) == 0) { q.maskW[p >> 5] = balW; q.maskX[p >> 5] = balX; q.maskA[p >> 5] = balA; }
+}
+
+template <int UV, int ROWS>
+__global__ void __launch_bounds__(ST_WALK_BLOCK)
+k_walk(const AdvectGrid g, const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ ic,
+       BuoyState s, StepOut o, WalkScratch q, int ntiles)
+{
+    constexpr int T = ST_WALK_TILES;
+    static_assert(T <= 32, "one warp scans the ballot words of a block");
+    __shared__ unsigned sMask[2][T];
+    __shared__ int sPre[2][T + 1];                                // exclusive prefix of the counts: W, then X
+    const int tile0 = (int)blockIdx.x * T;
+    if (threadIdx.x < 32) {
+        const int t = tile0 + (int)threadIdx.x;
+        const bool in = (int)threadIdx.x < T && t < ntiles;
+        const unsigned mw = in ? q.maskW[t] : 0u, mx = (in && UV == 1) ? q.maskX[t] : 0u;
+        if (o.n_alive) {                                          // buoys that were alive when the step began
+            const int na = __reduce_add_sync(0xffffffffu, in ? __popc(q.maskA[t]) : 0);
+            if (threadIdx.x == 0 && na) atomicAdd(o.n_alive, (unsigned long long)na);
+        }
+        int cw = __popc(mw), cx = __popc(mx);
+        int iw = cw, ix = cx;                                     // inclusive warp scans
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int aw = __shfl_up_sync(0xffffffffu, iw, d), ax = __shfl_up_sync(0xffffffffu, ix, d);
+            if ((int)threadIdx.x >= d) { iw += aw; ix += ax; }
+        }
+        if (threadIdx.x < T) {
+            sMask[0][threadIdx.x] = mw; sMask[1][threadIdx.x] = mx;
+            sPre[0][threadIdx.x + 1] = iw; sPre[1][threadIdx.x + 1] = ix;
+        }
+        if (threadIdx.x == 0) { sPre[0][0] = 0; sPre[1][0] = 0; }
+    }
+    __syncthreads();
+    const int nW = sPre[0][T], nX = sPre[1][T];
+    const int Ni = g.Ni;
+    for (int e = threadIdx.x; e < nW + nX; e += ST_WALK_BLOCK) {
+        const int kind = e >= nW;                                 // 0: W entry, 1: X entry
+        const int r = kind ? e - nW : e;
+        int lo = 0;                                               // tile whose prefix range holds r
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+            if (lo + step < T && sPre[kind][lo + step] <= r) lo += step;
+        const unsigned lane_of = __fns(sMask[kind][lo], 0, r - sPre[kind][lo] + 1);
+        const unsigned p = (unsigned)(tile0 + lo) * 32u + lane_of;
+        if (kind == 0) {
+            const pt A = ld_stream_pt(q.P + p), B = ld_stream_pt(s.pos + p);
+            int2 cc = __ldcs(s.cell + p);
             const int j0 = cc.x, i0 = cc.y;
-            int8_t a2 = 1;
-            pt A, B;
-            { const double2 q = *reinterpret_cast<const double2*>(&qP[e]); A.y = q.x; A.x = q.y; }
-            { const double2 q = *reinterpret_cast<const double2*>(&qPn[e]); B.y = q.x; B.x = q.y; }
             const int c = cc.x * Ni + cc.y;
             if (!inside_quad_flat(B.y, B.x, ldg_pt(g.F, c - Ni - 1), ldg_pt(g.F, c - Ni), ldg_pt(g.F, c),
                                   ldg_pt(g.F, c - 1))) {
+                int8_t a2 = 1;
                 walk_cell(g, ic, A, B, cc.x, cc.y, a2);
-                const unsigned p = qI[e];
                 if (!a2) cc.x |= ST_DEAD_BIT;
                 if (cc.x != j0 || cc.y != i0) __stcs(s.cell + p, cc);
                 if (!a2) s.alive[p] = 0;
             }
+        } else {
+            if (UV == 1) exact_lane<UV, ROWS>(g, u, v, ic, s, o, q, p);
         }
-        __syncwarp();
-    };
-    auto exact_pass = [&](int lo, int n) {                        // dense X pass: nothing certified
-        __syncwarp();
-        if (lane < n) exact_lane<UV, ROWS>(g, u, v, ic, s, o, qX[lo + lane]);
-        __syncwarp();
-    };
-
-    const int tile0 = (int)blockIdx.x;
-    if (lane == 0) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) mbar_init(&bars[d], 1);
-        fence_mbar_init();
-#pragma unroll
-        for (int d = 0; d < D; ++d) issue(tile0 + d * nwarps, d);
-    }
-    __syncwarp();
-    mbar_wait(&bars[0], 0);
-    CertGather G = gather(tile0, 0);
-    int st = 0, ph = 0;                                           // ring stage of the current tile, its mbarrier phase
-    int qn = 0, xn = 0, my_alive = 0;
-    for (int tile = tile0; tile < ntiles; tile += nwarps) {
-        const long long p = (long long)tile * 32 + lane;
-        const bool valid = p < s.nP;
-        // gathers of the NEXT tile (its state landed one or two tiles ago): in flight during this tile
-        const int st1 = (st + 1 == D) ? 0 : st + 1, ph1 = (st + 1 == D) ? ph ^ 1 : ph;
-        CertGather Gn = G;
-        if (tile + nwarps < ntiles) {
-            mbar_wait(&bars[st1], ph1);
-            Gn = gather(tile + nwarps, st1);
-        }
-        pt P;
-        { const double2 q = *reinterpret_cast<const double2*>(ring[st] + lane * sizeof(pt)); P.y = q.x; P.x = q.y; }
-        const int2 c2 = *reinterpret_cast<const int2*>(ring[st] + POS_B + lane * sizeof(int2));
-        const bool al = valid && c2.x >= 0;
-        my_alive += al;
-        bool active = al;
-        bool prestart = false;
-        if (WIN && active) {
-            const int f = s.rec_first[p], l = s.rec_last[p];
-            prestart = (jrec + 1 == f);
-            active = (jrec >= f) && (jrec <= l);
-        }
-        pt Pn;
-        const CertLane cl = cert_eval<UV>(G.f0, G.f1, G.mw, P, G.uL, G.uR, G.vB, G.vT, g.rdt, kdt, Pn);
-        const bool goX = active && !cl.pick_ok;                   // the reference's own step decides everything
-        const bool goW = active && cl.pick_ok && !cl.in_ok;       // Pn is final; inside test + walk by the reference's tests
-        pt outp = {ST_FILL, ST_FILL};
-        int8_t m = 0;
-        if (active) {
-            outp = Pn; m = 1;
-            if (!goX) st_stream_pt(s.pos + p, outp);
-        } else if (WIN && prestart) {
-            outp = P; m = 1;
-        }
-        if (valid) {
-            if (o.mask) __stcs(o.mask + p, m);
-            if (!goX) {
-                if (ROWS == 0) { if (o.yx) st_stream_pt(o.yx + p, outp); }
-                else           { if (o.yx) put_row_yx(o, p, outp); }
-                if (o.latlon) {
-                    pt ll; ll.y = g.proj.fill_lat; ll.x = g.proj.fill_lon;            // :493 on a fill row
-                    if (m) ll = inv_stere_fast(outp, g.proj, g.atab);
-                    if (ROWS == 0) st_stream_pt(o.latlon + p, ll);
-                    else           put_row_pt(o.latlon, p, ll, o.f4);
-                }
-            }
-        }
-        const unsigned balW = __ballot_sync(0xffffffffu, goW);
-        if (goW) {
-            const int e = qn + __popc(balW & lt);
-            *reinterpret_cast<double2*>(&qP[e]) = make_double2(P.y, P.x);
-            *reinterpret_cast<double2*>(&qPn[e]) = make_double2(outp.y, outp.x);
-            qC[e] = c2; qI[e] = (unsigned)p;
-        }
-        qn += __popc(balW);
-        // this tile's stage is free: every lane has read it (ballot above converged the warp)
-        if (lane == 0) issue(tile + D * nwarps, st);
-        if (qn >= 32) { qn -= 32; walk_pass(qn, 32); }
-        if (UV == 1) {
-            const unsigned balX = __ballot_sync(0xffffffffu, goX);
-            if (balX) {                                           // warp-uniform, rare
-                if (goX) qX[xn + __popc(balX & lt)] = (unsigned)p;
-                xn += __popc(balX);
-                if (xn >= 32) { xn -= 32; exact_pass(xn, 32); }
-            }
-        }
-        G = Gn; st = st1; ph = ph1;
-    }
-    walk_pass(0, qn);
-    if (UV == 1) exact_pass(0, xn);
-    if (o.n_alive) {
-        const int wsum = __reduce_add_sync(0xffffffffu, my_alive);
-        if (lane == 0 && wsum) atomicAdd(o.n_alive, (unsigned long long)wsum);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // k_cell_frames: the frame and the margins of every host cell, once per grid (st_create).  FP64 throughout;
 // see the head of this file for what is verified.  Output per cell c = jT*Ni + iT:
-//   frames[2c]   = {oy, ox, a, b}     frames[2c+1] = {c, d, es, et}     (f32; s = a dx + b dy + es, t = c dx + d dy + et)
-//   fmargin[c]   = bf16(hin) << 16 | bf16(msep)   (hin rounded down, msep rounded up; hin = -1: never certify)
+//   frames[2c]   = {oy, ox, a, b}     frames[2c+1] = {c, d, mw, ew}     (f32; s = a dx + b dy + es, t = c dx + d dy + et)
+//   mw = bf16(hin) << 16 | bf16(msep)   (hin rounded down, msep rounded up; hin = -1: never certify)
+//   ew = bf16(es) << 16 | bf16(et)      (the offsets that centre the frame, truncated to bf16: 32 B per cell, one sector)
 // stats[0] = cells admitted, stats[1] = cells examined.
 // ---------------------------------------------------------------------------------------------------
 struct FramePt { double s, t; };
@@ -337,8 +313,7 @@ __device__ __forceinline__ unsigned bf16_up(float x)             // smallest bf1
 }
 
 __global__ void __launch_bounds__(ST_BLOCK)
-k_cell_frames(const AdvectGrid g, float4* __restrict__ frames, unsigned* __restrict__ fmargin,
-              unsigned long long* __restrict__ stats)
+k_cell_frames(const AdvectGrid g, float4* __restrict__ frames, unsigned long long* __restrict__ stats)
 {
     const long long c = (long long)blockIdx.x * ST_BLOCK + threadIdx.x;
     const long long n = (long long)g.Nj * g.Ni;
@@ -361,7 +336,9 @@ k_cell_frames(const AdvectGrid g, float4* __restrict__ frames, unsigned* __restr
         bool ok = det > 0.0 && isfinite(det);
         const float af = (float)(ety / det), bf = (float)(-etx / det), cf = (float)(-esy / det), df = (float)(esx / det);
         const double a = af, b = bf, cc = cf, d = df;             // the frame IS these f32 numbers
-        const float esf = (float)(-(a * (cx - ox) + b * (cy - oy))), etf = (float)(-(cc * (cx - ox) + d * (cy - oy)));
+        // (truncated to bf16: like a..d these numbers DEFINE the frame, everything below is measured in it)
+        const float esf = __uint_as_float(__float_as_uint((float)(-(a * (cx - ox) + b * (cy - oy)))) & 0xffff0000u);
+        const float etf = __uint_as_float(__float_as_uint((float)(-(cc * (cx - ox) + d * (cy - oy)))) & 0xffff0000u);
         const double es0 = esf, et0 = etf;
         const double detM = a * d - b * cc;
         ok = ok && detM > 0.0 && isfinite(detM);
@@ -444,13 +421,15 @@ k_cell_frames(const AdvectGrid g, float4* __restrict__ frames, unsigned* __restr
             }
         }
         if (hin_f > 0.0f) {
-            o0 = make_float4(oyf, oxf, af, bf); o1 = make_float4(cf, df, esf, etf);
             mw = (__float_as_uint(hin_f) & 0xffff0000u) | (__float_as_uint(msep_f) >> 16);
+            o0 = make_float4(oyf, oxf, af, bf);
+            o1 = make_float4(cf, df, __uint_as_float(mw), __uint_as_float(__float_as_uint(esf) | (__float_as_uint(etf) >> 16)));
             atomicAdd(stats, 1ull);
         }
         atomicAdd(stats + 1, 1ull);
     }
-    frames[2 * c] = o0; frames[2 * c + 1] = o1; fmargin[c] = mw;
+    if (mw == NEVER) o1.z = __uint_as_float(NEVER);
+    frames[2 * c] = o0; frames[2 * c + 1] = o1;
 }
 
 }  // namespace st
@@ -473,7 +452,7 @@ k_cert_selftest(const AdvectGrid g, long long n, const pt* __restrict__ yx, cons
     const float4 w = vel[p];                                       // uL, uR, vB, vT
     const float kdt = __double2float_rn(g.rdt / 1000.0);
     pt Pn;
-    const CertLane cl = cert_eval<UV>(g.frames[2 * (size_t)c], g.frames[2 * (size_t)c + 1], g.fmargin[c], P,
+    const CertLane cl = cert_eval<UV>(g.frames[2 * (size_t)c], g.frames[2 * (size_t)c + 1], P,
                                       w.x, w.y, w.z, w.w, g.rdt, kdt, Pn);
     const pt bl = g.F[c - Ni - 1], br = g.F[c - Ni], ul = g.F[c - 1], ur = g.F[c];
     bool llum1 = false, llvm1 = false;

@@ -250,30 +250,40 @@ __device__ __forceinline__ double rsqrt_nr(double x)
 // octant o = swap | (c<0)<<1 | (s<0)<<2: the direction's angle from the +c axis towards +s is
 //   swap=0,c>=0: +-theta   swap=1,c>=0: +-(pi/2 - theta)   swap=0,c<0: +-(pi - theta)   swap=1,c<0: +-(pi/2 + theta)
 // with the sign of s.
+// SM: `tab` is a shared-memory copy of the table (k_advect_cert: the lookup then never queues behind the global loads)
+template <bool SM = false>
 __device__ __forceinline__ double folded_angle(double s, double c, const AngEntry* __restrict__ tab, int& oct)
 {
     const bool swp = fabs(s) > fabs(c);
     const double ms = swp ? c : s, Ms = swp ? s : c;           // signed; magnitudes taken at the uses
     int j = __double2int_rn(fabs(ms) * (double)ST_ANG_STEPS);
     j = min(max(j, 0), ST_ANG_LAST);
-    const double2 e0 = __ldg(reinterpret_cast<const double2*>(tab + j));          // alpha, cos
-    const double sa = __ldg(reinterpret_cast<const double*>(tab + j) + 2);         // sin
+    double2 e0; double sa;                                                        // alpha, cos; sin
+    if (SM) {
+        e0 = *reinterpret_cast<const double2*>(tab + j);
+        sa = tab[j].sa;
+    } else {
+        e0 = __ldg(reinterpret_cast<const double2*>(tab + j));
+        sa = __ldg(reinterpret_cast<const double*>(tab + j) + 2);
+    }
     const double sd = fma(fabs(ms), e0.y, -(fabs(Ms) * sa));                      // sin(delta), |delta| < 0.011
     const double z = sd * sd;
     const double d = fma(sd * z, fma(z, 3. / 40., 1. / 6.), sd);                  // asin: next term 15/336 sd^7 < 1e-15 rad
     oct = (int)swp | ((int)(c < 0.0) << 1) | ((__double2hiint(s) >> 31) & 1) << 2;
     return e0.x + d;
 }
+template <bool SM = false>
 __device__ __forceinline__ double angle_of_unit(double s, double c, const AngEntry* __restrict__ tab)
 {
     const double HALFPI = 1.5707963267948966, PI = 3.141592653589793;
     int oct;
-    double th = folded_angle(s, c, tab, oct);
+    double th = folded_angle<SM>(s, c, tab, oct);
     if (oct & 1) th = HALFPI - th;
     if (oct & 2) th = PI - th;
     return copysign(th, s);
 }
 
+template <bool SM = false>
 __device__ __forceinline__ pt inv_stere_fast(pt yx, const ProjConst& pc, const AngEntry* __restrict__ tab)
 {
     const double R2D = 57.29577951308232;
@@ -294,7 +304,7 @@ __device__ __forceinline__ pt inv_stere_fast(pt yx, const ProjConst& pc, const A
         const double inv = rcp_nr(1.0 + t2);
         const double s = (1.0 - t2) * inv;              // sin(chi)
         const double c = (t + t) * inv;                 // cos(chi)
-        const double chi = angle_of_unit(s, c, tab);
+        const double chi = angle_of_unit<SM>(s, c, tab);
         const double s2 = (s + s) * c;                  // sin(2 chi)
         const double c2x2 = fma(-4.0 * s, s, 2.0);      // 2 cos(2 chi)
         double b2 = 0.0, b1 = pc.c[4];                  // c[5] = 6e-16 rad is dropped
@@ -303,7 +313,7 @@ __device__ __forceinline__ pt inv_stere_fast(pt yx, const ProjConst& pc, const A
         r.y = fma(b1, s2, chi) * R2D;
     }
     int oct;
-    const double th = folded_angle(yx.x * rinv, -(yx.y * rinv), tab, oct);
+    const double th = folded_angle<SM>(yx.x * rinv, -(yx.y * rinv), tab, oct);
     double lon = fma(th, pc.oct_sg[oct], pc.oct_off[oct]);
     if (pc.wrap_up) { if (lon > 180.0) lon -= 360.0; }
     else            { if (lon < -180.0) lon += 360.0; }

@@ -7,7 +7,7 @@ static cudaError_t launch_advect_experiment(const AdvectGrid& g, const float* u,
                                             const BuoyState& s, int jrec, const StepOut& o, int variant, cudaStream_t st)
 {
     const bool win = s.rec_first != nullptr;
-    // variants 4 and 9: the one-block-per-tile form of the tuned step (k_advect_step)
+    // variants 12 and 9: the one-block-per-tile form of the tuned step (k_advect_step)
 #define ST_LAUNCH(BLK_, MINB_)                                                                              \
     do {                                                                                                    \
         const dim3 gr((unsigned)((s.nP + BLK_ - 1) / BLK_)), bl(BLK_);                                       \
@@ -67,7 +67,7 @@ static cudaError_t launch_advect_experiment(const AdvectGrid& g, const float* u,
     }
     switch (variant) {
     case 9: ST_LAUNCH(256, 4); break;       // one block per tile, 256 threads
-    default: ST_LAUNCH(128, 10); break;     // variant 4: one block per tile, 128 threads x 10 blocks/SM
+    default: ST_LAUNCH(128, 10); break;     // variant 12: one block per tile, 128 threads x 10 blocks/SM
     }
 #undef ST_LAUNCH
     return cudaGetLastError();

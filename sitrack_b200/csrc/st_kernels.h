@@ -20,12 +20,20 @@ struct AdvectGrid {
                                 //  -- the buoy-independent orientation of the two U/V-pick segment tests (k_cell_bits);
                                 //  bit 2 = the cell is a convex anticlockwise quadrangle with edges shorter than 1024 km
     int filter_ok;              // the grid qualifies for the orientation filter of k_advect_warp (st_create checks)
-    // certified fast path (st_cert.cuh, k_cell_frames): per host cell an affine frame as 8 f32 and two bf16 margins
-    const float4* frames;       // (2*Nj*Ni) {oy, ox, a, b}, {c, d, es, et}
-    const unsigned* fmargin;    // (Nj*Ni) bf16(hin) << 16 | bf16(msep); hin = -1: nothing is certified in this cell
+    // certified fast path (st_cert.cuh, k_cell_frames): per host cell an affine frame and two margins, 32 B
+    const float4* frames;       // (2*Nj*Ni) {oy, ox, a, b}, {c, d, bf16(hin) << 16 | bf16(msep), bf16(es) << 16 | bf16(et)};
+                                // hin = -1: nothing is certified in this cell
     int frames_ok;              // frames were built (filter_ok and the build succeeded)
     ProjConst proj;
     const AngEntry* atab;       // 47-entry angle table of inv_stere_fast (device)
+};
+
+// Scratch between k_advect_cert and k_walk (st_cert.cuh), all of it rewritten by every step.
+struct WalkScratch {
+    pt* P;                      // (nP) position before the step of the lanes marked in maskW, at the buoy's own index
+    unsigned* maskW;            // (ceil(nP/32)) per tile of 32 buoys: lanes whose "still inside" is not certified
+    unsigned* maskX;            // (ceil(nP/32)) lanes whose U/V pick is not certified
+    unsigned* maskA;            // (ceil(nP/32)) lanes alive when the step began (k_walk sums them into n_alive)
 };
 
 // Buoy state, struct of arrays in HBM.
@@ -36,6 +44,7 @@ struct BuoyState {
     int8_t* alive;              // 1 alive, 0 discontinued
     const int32_t* rec_first;   // optional per-buoy record window (no -F); nullptr with -F
     const int32_t* rec_last;
+    WalkScratch q;              // q.P == nullptr: not allocated (variant 2 runs instead of the default step)
 };
 
 // One trajectory row (all nullable).
@@ -84,7 +93,7 @@ cudaError_t launch_advect_ext(const AdvectGrid& g, const float* u, const float* 
                               const BuoyState& s, int jrec, const StepOut& o, int scheme, int interp, int max_hops,
                               cudaStream_t st);
 cudaError_t launch_cell_bits(const AdvectGrid& g, int8_t* bits, int* n_bad_coord, cudaStream_t st);
-cudaError_t launch_cell_frames(const AdvectGrid& g, float4* frames, unsigned* fmargin, unsigned long long* stats, cudaStream_t st);
+cudaError_t launch_cell_frames(const AdvectGrid& g, float4* frames, unsigned long long* stats, cudaStream_t st);
 cudaError_t launch_cert_selftest(const AdvectGrid& g, long long n, const pt* yx, const int2* cell, const float4* vel,
                                  uint8_t* flags, cudaStream_t st);
 cudaError_t launch_divcore(const double* a, const double* b, double* q_fast, double* q_div, long long n, cudaStream_t st);

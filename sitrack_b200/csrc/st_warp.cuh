@@ -37,7 +37,11 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
         if (tile < ntiles && p < s.nP) {
             al = __ldcs(s.alive + p);
             P = ld_stream_pt(s.pos + p);
+#ifdef ST_CELL_CG
+            c2 = __ldcg(s.cell + p);                              // evict-normal: the sector is still in L2 when a walk pass rewrites 8 bytes of it
+#else
             c2 = __ldcs(s.cell + p);
+#endif
         }
     };
     auto walk_pass = [&](int lo, int n) {
@@ -60,7 +64,11 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
                 walk_cell(g, ic, A, B, cc.x, cc.y, a2);
                 const unsigned p = qI[wid][e];
                 if (!a2) cc.x |= ST_DEAD_BIT;
+#ifdef ST_CELL_CG
+                if (cc.x != j0 || cc.y != i0) __stcg(s.cell + p, cc);
+#else
                 if (cc.x != j0 || cc.y != i0) __stcs(s.cell + p, cc);
+#endif
                 if (!a2) s.alive[p] = 0;
             }
         }

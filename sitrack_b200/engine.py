@@ -104,8 +104,8 @@ class TrackEngine:
         self.close()
 
     def set_kernel_variant(self, variant):
-        """0 = k_advect_cert (default), 1 = k_advect_step_v1 (straightforward A/B reference), 2 / 3 =
-        k_advect_warp with / without the orientation filter; see include/sitrack_b200.h."""
+        """0 = 2 = k_advect_warp with the orientation filter (default), 3 without it, 1 = k_advect_step_v1
+        (straightforward A/B reference), 4 = the certified two-kernel step; see include/sitrack_b200.h."""
         check(self.L.st_set_kernel_variant(self.h, int(variant)), self.h)
 
     # -- diagnostics of the certified fast path (csrc/st_cert.cuh) ----------------------------

@@ -45,7 +45,7 @@ def scattered_seeds(grid, n, seed=2):
     return _pack(lat, lon, y, x)
 
 
-def dense_seeds(grid, n, ic0, seed=3, jitter=0.42, f4=False, with_latlon=True, box=None):
+def dense_seeds(grid, n, ic0, seed=3, jitter=0.42, f4=False, with_latlon=True, box=None, cells_out=None):
     """n buoys over the pack: random ocean T-cells with siconc>=0.9, jittered
     inside the cell, returned sorted by (j,i) (HSS1-with-replicas style)."""
     rng = np.random.default_rng(seed)
@@ -58,6 +58,8 @@ def dense_seeds(grid, n, ic0, seed=3, jitter=0.42, f4=False, with_latlon=True, b
     cells = np.flatnonzero(m)
     pick = np.sort(rng.choice(cells, size=n, replace=n > cells.size))
     jj, ii = np.divmod(pick, Ni)
+    if cells_out is not None:    # the T-cell each buoy was drawn in (CPU arm of bench.py: skips a nearest-point search)
+        cells_out["seed_cells"] = np.stack([jj, ii], axis=1)
     y, x = grid["warp"](jj + rng.uniform(-jitter, jitter, n), ii + rng.uniform(-jitter, jitter, n))
     if not with_latlon:          # caller derives lat/lon itself (e.g. on the device)
         return np.arange(n, dtype=np.int64) + 1, None, np.ascontiguousarray(np.stack([y, x], axis=1))

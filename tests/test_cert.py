@@ -1,12 +1,13 @@
-"""The certified fast path of the default step kernel (sitrack_b200/csrc/st_cert.cuh).
+"""The certified fast path of step variant 4 (sitrack_b200/csrc/st_cert.cuh: k_advect_cert + k_walk).
 
 k_advect_cert decides the U/V pick (si3_part_tracker.py:430-441) and "the buoy is still inside its cell"
-(sitrack/locate.py:49-78) from a 36-byte per-cell frame in f32 whenever the buoy is farther than per-cell
-margins from every line involved; everything else runs the reference's own tests.  These tests attack the
+(sitrack/locate.py:49-78) from a 32-byte per-cell frame in f32 whenever the buoy is farther than per-cell
+margins from every line involved; everything else runs the reference's own tests in k_walk.  These tests attack the
 claim "certified => equal to the reference's decision" directly: st_selftest_cert evaluates, for arbitrary
 (position, cell, velocities), the certified decision next to the exact one (the same device predicates that
 tests/test_gpu_parity.py pins against the reference's golden vectors), with positions placed ON the margins.
-The bit-exact trajectory tests of tests/test_gpu_parity.py all run through the same kernel."""
+The bit-exact trajectory tests of tests/test_gpu_parity.py run variant 4 next to the default kernel, and
+test_cert_step_vs_default_at_size compares the two on a cloud large enough to mark tens of thousands of lanes."""
 import numpy as np
 import pytest
 
@@ -168,3 +169,37 @@ def test_cert_rejects_bad_cells(torch, gold_track):
             far[k] = far[k] + 262144.0
     with engine_for(far) as eng:
         assert eng.cert_stats() == (0, 0)
+
+
+def test_cert_step_vs_default_at_size(torch):
+    """400 k buoys x 12 records on the NANUK4-shaped grid, 3x faster ice: the certified two-kernel step (variant 4)
+    against the default kernel, record by record: rows, masks, alive counts and final state bit-identical."""
+    import synth
+    g = synth.make_grid(**synth.GRID_PRESETS["nanuk4"], seed=0)
+    nrec = 12
+    U, V, IC = synth.make_records(g, nrec, seed=3)
+    U *= np.float32(3.0); V *= np.float32(3.0)
+    ids, SG, SC = synth.hss_seeds(g, IC[0], khss=1)
+    rng = np.random.default_rng(11)
+    rep = int(np.ceil(400_000 / SC.shape[0]))
+    res = {}
+    for variant in (0, 4):
+        with engine_for(g) as eng:
+            eng.set_locate_grid(g["latT"], g["lonT"], g["ResKM"])
+            cell, near, keep = eng.seed_locate(SG, SC, IC[0])
+            ik = np.flatnonzero(keep)
+            pos0 = np.repeat(SC[ik], rep, axis=0)
+            cell0 = np.repeat(cell[ik], rep, axis=0)
+            # jitter inside the cell: a few hundred metres (stays inside on the 12.5 km grid)
+            pos0 = pos0 + np.random.default_rng(12).uniform(-1.5, 1.5, pos0.shape)
+            eng.set_kernel_variant(variant)
+            eng.set_buoys(pos0, cell0)
+            r = eng.track((U, V, IC), nrec, pos0=pos0)
+            res[variant] = (r, eng.get_state())
+    r0, s0 = res[0]; r4, s4 = res[4]
+    assert np.array_equal(r0["posC"], r4["posC"]) and np.array_equal(r0["mask"], r4["mask"])
+    assert np.array_equal(r0["n_alive"], r4["n_alive"])
+    assert np.abs(r0["posG"][1:] - r4["posG"][1:]).max() == 0.0
+    for a, b in zip(s0, s4):
+        assert np.array_equal(a, b)
+    assert r0["n_alive"][-1] < r0["n_alive"][0]                  # the run does kill buoys
