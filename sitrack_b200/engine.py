@@ -226,7 +226,15 @@ class TrackEngine:
     def upload_record(self, slot, host_rec, stream=None):
         """Async H2D of a whole record from caller-owned host memory: a pinned torch tensor or
         a C-contiguous numpy array (3,Nj,Ni) f4 laid out [u_ice, v_ice, siconc]."""
-        ptr = host_rec.data_ptr() if hasattr(host_rec, "data_ptr") else hptr(host_rec)
+        if hasattr(host_rec, "data_ptr"):
+            if str(host_rec.dtype) != "torch.float32" or not host_rec.is_contiguous():
+                raise TypeError("upload_record: the record must be a contiguous float32 tensor (3,Nj,Ni)")
+            ptr = host_rec.data_ptr()
+        else:
+            if host_rec.dtype != np.float32 or not host_rec.flags["C_CONTIGUOUS"]:
+                raise TypeError("upload_record: the record must be a C-contiguous float32 array (3,Nj,Ni); "
+                                "the reference's f8 work arrays (si3_part_tracker.py:199-202) need .astype('f4')")
+            ptr = hptr(host_rec)
         check(self.L.st_upload_record(self.h, slot, ptr, _sptr(stream)), self.h)
 
     # -- the step ----------------------------------------------------------------------
@@ -260,6 +268,9 @@ class TrackEngine:
         out_latlon arrays select the file-dtype rows (ncio.py:153-159)."""
         na = C.c_int64(0)
         fn = self.L.st_track_record_host_f4 if _rows_f4(out_yx, out_latlon) else self.L.st_track_record_host
+        # the fields are f4 like the netCDF variables; the reference's f8 work arrays (si3_part_tracker.py:199-202)
+        # hold exactly those values, so the cast back is lossless
+        u, v, ic = as_c(u, np.float32), as_c(v, np.float32), as_c(ic, np.float32)
         check(fn(self.h, int(jrec), hptr(u), hptr(v), hptr(ic), hptr(out_yx),
                  hptr(out_latlon), hptr(out_mask), C.byref(na) if want_alive else None),
               self.h)
@@ -358,6 +369,7 @@ class TrackEngine:
         d_ll = [torch.empty((nP, 2), dtype=rdt, device=dev) for _ in range(NB)] if want_latlon else [None] * NB
         d_mk = [torch.empty((nP,), dtype=torch.int8, device=dev) for _ in range(NB)]
         d_na = torch.zeros((nrec,), dtype=torch.int64, device=dev)
+        s_cmp.wait_stream(torch.cuda.current_stream(dev))      # the zero fill above ran on torch's current stream
         keep = sink is None
         if keep:
             posC = torch.full((nrec + 1, nP, 2), FillValue, dtype=rdt).pin_memory()
@@ -464,6 +476,7 @@ def _track_chunked(self, get, nrec, kstrt, pos0, posG0, rec_first, want_latlon, 
     d_ll = [torch.empty((chunk, nP, 2), dtype=rdt, device=dev) for _ in range(2)] if want_latlon else [None, None]
     d_mk = [torch.empty((chunk, nP), dtype=torch.int8, device=dev) for _ in range(2)]
     d_na = torch.zeros((nrec,), dtype=torch.int64, device=dev)
+    s_cmp.wait_stream(torch.cuda.current_stream(dev))          # the zero fill above ran on torch's current stream
     posC = torch.full((nrec + 1, nP, 2), FillValue, dtype=rdt).pin_memory()
     posG = torch.full((nrec + 1, nP, 2), FillValue, dtype=rdt).pin_memory()
     mask = torch.zeros((nrec + 1, nP), dtype=torch.int8).pin_memory()

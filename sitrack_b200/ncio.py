@@ -83,9 +83,17 @@ def open_dataset(fn):
 
 
 def _plane(var):
-    """The horizontal (Nj,Ni) plane of a mesh_mask variable: leading singleton axes dropped."""
-    a = np.asarray(var[:])
-    return a.reshape(a.shape[-2:])
+    """The horizontal (Nj,Ni) plane of a mesh_mask variable: first time record / first level, as the reference
+    indexes them (ncio.py:28-36: `[0,0,:,:]` for the masks, `[0,:,:]` for coordinates and scale factors).  A real
+    NEMO mesh_mask stores tmask / fmask as (t,z,y,x) with z > 1; only the surface plane is read."""
+    nd = len(var.shape)
+    return np.asarray(var[(0,) * (nd - 2) + (slice(None), slice(None))])
+
+
+def _keep_mask(a):
+    """netCDF4 hands out masked arrays; keep the mask when it hides something (the reference does, and its
+    np.min / np.max then skip the fill values, ncio.py:341), plain ndarray otherwise."""
+    return a if isinstance(a, np.ma.MaskedArray) and np.ma.is_masked(a) else np.asarray(a)
 
 
 def _read_planes(fn, names):
@@ -224,11 +232,11 @@ def LoadNCtime(cfile, ltime2d=False, iverbose=0):
         Nt = ds.dimensions['time'].size
         _check_tunits(ds.variables['time'], 'LoadNCtime')
         print('    * [LoadNCtime] => reading "time" (%d records) in file %s' % (Nt, os.path.basename(cfile)))
-        t1d = np.asarray(ds.variables['time'][:])
+        t1d = _keep_mask(ds.variables['time'][:])
         if not ltime2d:
             return Nt, t1d
         _check_tunits(ds.variables['time_pos'], 'LoadNCtime')
-        t2d = np.asarray(ds.variables['time_pos'][:, :])
+        t2d = _keep_mask(ds.variables['time_pos'][:, :])
     if t2d.shape[0] != Nt:
         _die(' ERROR [LoadNCtime()]: array `time_pos` has not the same number of records as `time`!!!')
     return Nt, t1d, t2d

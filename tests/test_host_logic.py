@@ -92,3 +92,47 @@ def test_row_dtype_selection_and_numa_binding_helpers():
     assert bind_host_to_gpu(10 ** 6) is None                     # no such device: no binding, no exception
     b = shard_bounds(636, 2)                                     # the CLI's torchrun test: 512 + 124 buoys
     assert b.tolist() == [0, 512, 636]
+
+
+def test_mesh_mask_with_levels_and_masked_time_pos(tmp_path, monkeypatch):
+    """(a) a real NEMO mesh_mask stores tmask/fmask as (t,z,y,x) with z > 1 -- only the surface plane is
+    read (reference ncio.py:28-36); (b) a `time_pos` with fill entries stays masked, so the seed file's time span
+    skips them like the reference's np.min / np.max on the masked array (ncio.py:341)."""
+    import sitrack_b200.ncio as ncio
+
+    class V:
+        def __init__(self, a, units=None):
+            self.a, self.units, self.shape = a, units, a.shape
+
+        def __getitem__(self, k):
+            return self.a[k]
+
+    class DS:
+        def __init__(self, variables, dims):
+            self.variables = variables
+            self.dimensions = {k: type("D", (), {"size": v})() for k, v in dims.items()}
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *e):
+            pass
+
+    rng = np.random.default_rng(0)
+    nz, Nj, Ni = 3, 5, 6
+    tm = (rng.random((1, nz, Nj, Ni)) > 0.3).astype('i1')
+    ds = DS({"tmask": V(tm), "glamt": V(rng.random((1, Nj, Ni)))}, {})
+    assert np.array_equal(ncio._plane(ds.variables["tmask"]), tm[0, 0])
+    assert np.array_equal(ncio._plane(ds.variables["glamt"]), ds.variables["glamt"].a[0])
+    assert np.array_equal(ncio._plane(V(tm[0, 0])), tm[0, 0])
+
+    t = np.array([1000, 4600], dtype='i4')
+    tp = np.ma.masked_equal(np.array([[1000, 1200, -9999], [4600, -9999, 4000]], dtype='i4'), -9999)
+    fake = DS({"time": V(t, ncio.tunits_default), "time_pos": V(tp, ncio.tunits_default)}, {"time": 2})
+    monkeypatch.setattr(ncio, "open_dataset", lambda fn: fake)
+    monkeypatch.setattr(ncio, "chck4f", lambda fn: None)
+    Nt, t1d, t2d = ncio.LoadNCtime("x.nc", ltime2d=True)
+    assert Nt == 2 and np.ma.is_masked(t2d)
+    assert int(np.min(t2d)) == 1000 and int(np.max(t2d)) == 4600
+    first, last, name, batch, _ = ncio.SeedFileTimeInfo("a_b_c_d.nc", ltime2d=True)
+    assert first == 0 and last == 7200                             # floor / ceil to the hour of 1000 .. 4600, not of -9999
