@@ -82,7 +82,15 @@ int  st_set_projection(st_ctx *ctx, double lat_ts_deg, double lon0_deg);
 int  st_set_locate_grid(st_ctx *ctx, const double *latT, const double *lonT, const double *resKM);
 int  st_seed_locate(st_ctx *ctx, int64_t nP, const double *SG, const double *SC, const float *ic0,
                     int32_t *cell, int32_t *nearest, int8_t *keep);
-/* Same with device pointers, ASYNC on `stream` (ic0_dev (Nj,Ni) f4 on the device).      */
+/* The same with the near-tie report (locate.py:253-266, util.py:85-103): CUDA's sin/cos/asin
+ * and numpy's differ in the last ulp, so a nearest point or an acceptance decided by less than 1e-11 relative is
+ * flagged for the caller to re-evaluate with numpy (sitrack_b200/engine.py does): flag (nP) bit 0 = the runner-up
+ * is within 1e-11 of the nearest, bit 1 = the distance is within 1e-11 of the acceptance radius; first (nP) = flat
+ * index of the nearest T-point before the acceptance test (-1 none in reach), second (nP) = flat index of the
+ * runner-up when bit 0 is set, else -1.  flag may be NULL (then so must first and second).                    */
+int  st_seed_locate_ex(st_ctx *ctx, int64_t nP, const double *SG, const double *SC, const float *ic0,
+                       int32_t *cell, int32_t *nearest, int8_t *keep, int8_t *flag, int32_t *first, int32_t *second);
+/* Same as st_seed_locate with device pointers, ASYNC on `stream` (ic0_dev (Nj,Ni) f4 on the device).      */
 int  st_seed_locate_dev(st_ctx *ctx, int64_t nP, const double *SG_dev, const double *SC_dev,
                         const float *ic0_dev, int32_t *cell_dev, int32_t *nearest_dev, int8_t *keep_dev,
                         void *stream);

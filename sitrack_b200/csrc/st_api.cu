@@ -393,33 +393,36 @@ int st_seed_locate_dev(st_ctx* c, int64_t nP, const double* SG, const double* SC
     return ST_OK;
 }
 
-int st_seed_locate(st_ctx* c, int64_t nP, const double* SG, const double* SC, const float* ic0,
-                   int32_t* cell, int32_t* nearest, int8_t* keep)
+int st_seed_locate_ex(st_ctx* c, int64_t nP, const double* SG, const double* SC, const float* ic0,
+                      int32_t* cell, int32_t* nearest, int8_t* keep, int8_t* flag, int32_t* first, int32_t* second)
 {
     if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
     if (!c->has_locate) return fail(c, ST_ESTATE, "st_seed_locate: call st_set_locate_grid first");
     if (nP < 0 || !SG || !SC || !ic0 || !cell || !keep) return fail(c, ST_EINVAL, "st_seed_locate: NULL argument");
+    if ((first || second) && !flag) return fail(c, ST_EINVAL, "st_seed_locate_ex: first/second come with flag");
     if (nP == 0) return ST_OK;
     CU(c, cudaSetDevice(c->device));
     const size_t n = (size_t)c->Nj * c->Ni;
-    double *dSG = nullptr, *dSC = nullptr; float* dic = nullptr; int32_t *dcell = nullptr, *dnear = nullptr; int8_t* dkeep = nullptr;
-    int rc = ST_OK;
-    cudaError_t e = upload(&dSG, SG, (size_t)2 * nP);
-    if (e == cudaSuccess) e = upload(&dSC, SC, (size_t)2 * nP);
-    if (e == cudaSuccess) e = upload(&dic, ic0, n);
-    if (e == cudaSuccess) e = cudaMalloc(&dcell, sizeof(int32_t) * 2 * nP);
-    if (e == cudaSuccess) e = cudaMalloc(&dnear, sizeof(int32_t) * 2 * nP);
-    if (e == cudaSuccess) e = cudaMalloc(&dkeep, (size_t)nP);
-    if (e == cudaSuccess) {
-        rc = st_seed_locate_dev(c, nP, dSG, dSC, dic, dcell, dnear, dkeep, c->stream);
-        if (rc == ST_OK) e = cudaStreamSynchronize(c->stream);
-    }
-    if (e == cudaSuccess && rc == ST_OK) e = cudaMemcpy(cell, dcell, sizeof(int32_t) * 2 * nP, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && rc == ST_OK && nearest) e = cudaMemcpy(nearest, dnear, sizeof(int32_t) * 2 * nP, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && rc == ST_OK) e = cudaMemcpy(keep, dkeep, (size_t)nP, cudaMemcpyDeviceToHost);
-    cudaFree(dSG); cudaFree(dSC); cudaFree(dic); cudaFree(dcell); cudaFree(dnear); cudaFree(dkeep);
-    if (e != cudaSuccess) return cuda_fail(c, e, "st_seed_locate");
-    return rc;
+    Scratch s; double *dSG, *dSC; float* dic; int32_t *dcell, *dnear, *dfirst = nullptr, *dsec = nullptr; int8_t *dkeep, *dflag = nullptr;
+    CU(c, s.up(&dSG, SG, (size_t)2 * nP)); CU(c, s.up(&dSC, SC, (size_t)2 * nP)); CU(c, s.up(&dic, ic0, n));
+    CU(c, s.alloc(&dcell, (size_t)2 * nP)); CU(c, s.alloc(&dnear, (size_t)2 * nP)); CU(c, s.alloc(&dkeep, (size_t)nP));
+    if (flag) { CU(c, s.alloc(&dflag, (size_t)nP)); CU(c, s.alloc(&dfirst, (size_t)nP)); CU(c, s.alloc(&dsec, (size_t)nP)); }
+    SeedOut o{(int2*)dcell, (int2*)dnear, dkeep, nullptr, dflag, dfirst, dsec};
+    CU(c, launch_seed_locate(c->lg, c->grid, dic, nP, (const pt*)dSG, (const pt*)dSC, o, 1, 1, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(cell, dcell, sizeof(int32_t) * 2 * nP, cudaMemcpyDeviceToHost));
+    if (nearest) CU(c, cudaMemcpy(nearest, dnear, sizeof(int32_t) * 2 * nP, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(keep, dkeep, (size_t)nP, cudaMemcpyDeviceToHost));
+    if (flag) CU(c, cudaMemcpy(flag, dflag, (size_t)nP, cudaMemcpyDeviceToHost));
+    if (first) CU(c, cudaMemcpy(first, dfirst, sizeof(int32_t) * nP, cudaMemcpyDeviceToHost));
+    if (second) CU(c, cudaMemcpy(second, dsec, sizeof(int32_t) * nP, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_seed_locate(st_ctx* c, int64_t nP, const double* SG, const double* SC, const float* ic0,
+                   int32_t* cell, int32_t* nearest, int8_t* keep)
+{
+    return st_seed_locate_ex(c, nP, SG, SC, ic0, cell, nearest, keep, nullptr, nullptr, nullptr);
 }
 
 int st_nearest_point(st_ctx* c, int64_t n, const double* latlon, double rd_found_km, int max_itr,

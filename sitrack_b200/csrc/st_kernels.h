@@ -126,6 +126,9 @@ struct SeedOut {
     int2* nearest;              // nearest T-point or {-1,-1}  (nullable)
     int8_t* keep;               // kmask of SeedInit
     double* dmin;               // haversine distance to the nearest T-point (nullable)
+    int8_t* flag;               // (nullable) bit 0: argmin decided by < 1e-11 relative, bit 1: acceptance within 1e-11 of its radius
+    int* first;                 // (nullable, with flag) flat index of the nearest T-point before the acceptance test
+    int* second;                // (nullable, with flag) flat index of the runner-up when bit 0 is set, else -1
 };
 
 cudaError_t locate_build(int Nj, int Ni, const double* d_lat, const double* d_lon, const double* d_res,

@@ -156,43 +156,49 @@ struct NearestOpt {
     int accept_mode;        // >=0: number of x1.2 growths of the last accepted radius; -1 never; -2 always
 };
 
+// best and runner-up (the runner-up feeds the near-tie flag of k_seed_locate)
 __device__ __forceinline__ void scan_bin(const LocateGrid& lg, int b, double plat, double plon,
-                                         double& best_d, int& best_k)
+                                         double& best_d, int& best_k, double& sec_d, int& sec_k)
 {
     const int s = __ldg(lg.bin_start + b), e = __ldg(lg.bin_start + b + 1);
     for (int q = s; q < e; ++q) {
         const int k = __ldg(lg.bin_pts + q);
         const double d = haversine_km(plat, plon, __ldg(lg.latT + k), __ldg(lg.lonT + k));
-        if (d < best_d || (d == best_d && k < best_k)) { best_d = d; best_k = k; }
+        if (d < best_d || (d == best_d && k < best_k)) { sec_d = best_d; sec_k = best_k; best_d = d; best_k = k; }
+        else if (d < sec_d || (d == sec_d && k < sec_k)) { sec_d = d; sec_k = k; }
     }
 }
 
 // exact argmin of the Haversine distance over the whole grid, or best_k = -1 when
 // the nearest point is provably farther than r_accept_max.
+// CUDA's sin/cos/asin and numpy's differ in the last ulp, so an argmin or an acceptance decided by less than
+// ST_TIE_REL (relative) is not trusted: the search keeps going until everything unscanned is farther than
+// best * (1 + ST_TIE_REL), the runner-up is reported, and the host re-evaluates such seeds with numpy (locate.py).
+#define ST_TIE_REL 1e-11
 __device__ void nearest_hash(const LocateGrid& lg, double plat, double plon, double r_accept_max,
-                             double& best_d, int& best_k)
+                             double& best_d, int& best_k, double& sec_d, int& sec_k)
 {
     double px, py; plane_of(plat, plon, px, py);
     const double scale = sqrt((1.0 + px * px + py * py) * (1.0 + lg.q2max));
     int bx = (int)floor((px - lg.x0) * lg.inv_bin), by = (int)floor((py - lg.y0) * lg.inv_bin);
     bx = min(max(bx, 0), lg.nbx - 1); by = min(max(by, 0), lg.nby - 1);
-    best_d = INFINITY; best_k = -1;
+    best_d = INFINITY; best_k = -1; sec_d = INFINITY; sec_k = -1;
     const int rmax = max(max(bx, lg.nbx - 1 - bx), max(by, lg.nby - 1 - by));
     for (int r = 0; r <= rmax; ++r) {
         const int y0 = by - r, y1 = by + r, x0 = bx - r, x1 = bx + r;
         for (int yy = max(y0, 0); yy <= min(y1, lg.nby - 1); ++yy) {
             if (yy == y0 || yy == y1) {
                 for (int xx = max(x0, 0); xx <= min(x1, lg.nbx - 1); ++xx)
-                    scan_bin(lg, yy * lg.nbx + xx, plat, plon, best_d, best_k);
+                    scan_bin(lg, yy * lg.nbx + xx, plat, plon, best_d, best_k, sec_d, sec_k);
             } else {
-                if (x0 >= 0) scan_bin(lg, yy * lg.nbx + x0, plat, plon, best_d, best_k);
-                if (x1 < lg.nbx && x1 != x0) scan_bin(lg, yy * lg.nbx + x1, plat, plon, best_d, best_k);
+                if (x0 >= 0) scan_bin(lg, yy * lg.nbx + x0, plat, plon, best_d, best_k, sec_d, sec_k);
+                if (x1 < lg.nbx && x1 != x0) scan_bin(lg, yy * lg.nbx + x1, plat, plon, best_d, best_k, sec_d, sec_k);
             }
         }
         // lower bound on the distance of anything not scanned yet
         const double sh = fmin(r * lg.bin / scale * (1.0 - 1e-9), 1.0);
         const double d_bound = 2. * 6360. * asin(sh);
-        if (best_d <= d_bound) return;                          // argmin proven
+        if (best_d * (1.0 + ST_TIE_REL) <= d_bound) return;     // argmin proven, and every near-tie has been seen
         if (d_bound > r_accept_max) { if (best_d > r_accept_max) best_k = -1; if (best_k < 0) return; }
     }
 }
@@ -215,8 +221,20 @@ k_seed_locate(const LocateGrid lg, const AdvectGrid g, const float* __restrict__
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= nP) return;
     const pt ll = SG[p];                                      // [lat, lon]
-    double d; int k;
-    nearest_hash(lg, ll.y, ll.x, r_accept_max, d, k);
+    double d, d2; int k, k2;
+    nearest_hash(lg, ll.y, ll.x, r_accept_max, d, k, d2, k2);
+    if (o.flag) {                                             // decisions within ST_TIE_REL: the host re-evaluates with numpy
+        int8_t fl = 0;
+        if (k >= 0 && k2 >= 0 && d2 - d <= ST_TIE_REL * d2) fl |= 1;                 // argmin near-tie
+        if (k >= 0 && no.accept_mode >= 0) {
+            double rf = lg.resKM ? __dmul_rn(0.5, __ldg(lg.resKM + k)) : no.rd_found_km;
+            for (int q = 0; q < no.accept_mode; ++q) rf = __dmul_rn(1.2, rf);
+            if (fabs(d - rf) <= ST_TIE_REL * rf) fl |= 2;                            // acceptance near the threshold
+        }
+        o.flag[p] = fl;
+        if (o.second) o.second[p] = (fl & 1) ? k2 : -1;
+        if (o.first) o.first[p] = k;
+    }
     if (k >= 0 && !accept_nearest(lg, no, k, d)) k = -1;
     int jT = -1, iT = -1;
     int8_t keep = 0;

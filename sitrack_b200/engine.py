@@ -77,6 +77,7 @@ class TrackEngine:
             if a is not None and a.shape != (self.Nj, self.Ni):
                 raise ValueError("grid arrays must all have shape (Nj,Ni)")
         tm = as_c(tmask, np.int8)
+        self._tmask_host = tm
         h = C.c_void_p()
         check(self.L.st_create(C.byref(h), self.device, self.Nj, self.Ni, *[hptr(a) for a in arrs], hptr(tm),
                                self.uv_strategy, self.rdt, self.rmin_conc))
@@ -138,17 +139,54 @@ class TrackEngine:
         rk = None if resKM is None or np.shape(resKM) != (self.Nj, self.Ni) else as_c(resKM, np.float64)
         check(self.L.st_set_locate_grid(self.h, hptr(la), hptr(lo), hptr(rk)), self.h)
         self._has_locate = True
+        self._loc = (la, lo, rk)                               # host copies: the near-tie re-check of seed_locate
 
-    def seed_locate(self, SG, SC, ic0):
-        """-> (cell (nP,2) i4, nearest (nP,2) i4, keep (nP,) i1); SeedInit's loop on the device."""
+    def seed_locate(self, SG, SC, ic0, recheck=True, stats=None):
+        """-> (cell (nP,2) i4, nearest (nP,2) i4, keep (nP,) i1); SeedInit's loop on the device.
+
+        recheck: seeds whose nearest point or acceptance the device decided by less than 1e-11 relative (CUDA's
+        sin/cos/asin differ from numpy's in the last ulp) are re-evaluated here with numpy, i.e. with the reference's
+        own arithmetic (locate.py:253-266, util.py:85-103); where that changes the nearest point, Survive and
+        FindContainingCell are redone for the seed.  stats (a dict) receives the counts."""
         SG, SC = as_c(SG, np.float64), as_c(SC, np.float64)
         ic0 = as_c(ic0, np.float32)
         nP = SG.shape[0]
         cell = np.zeros((nP, 2), np.int32)
         near = np.zeros((nP, 2), np.int32)
         keep = np.zeros(nP, np.int8)
-        check(self.L.st_seed_locate(self.h, nP, hptr(SG), hptr(SC), hptr(ic0), hptr(cell), hptr(near), hptr(keep)),
-              self.h)
+        if not recheck:
+            check(self.L.st_seed_locate(self.h, nP, hptr(SG), hptr(SC), hptr(ic0), hptr(cell), hptr(near), hptr(keep)),
+                  self.h)
+            return cell, near, keep
+        flag = np.zeros(nP, np.int8); first = np.zeros(nP, np.int32); second = np.zeros(nP, np.int32)
+        check(self.L.st_seed_locate_ex(self.h, nP, hptr(SG), hptr(SC), hptr(ic0), hptr(cell), hptr(near), hptr(keep),
+                                       hptr(flag), hptr(first), hptr(second)), self.h)
+        idx = np.flatnonzero(flag)
+        changed = 0
+        if idx.size:
+            from .locate import _recheck_nearest
+            la, lo, rk = self._loc
+            redo = []
+            for p in idx:
+                ji = _recheck_nearest(SG[p], int(first[p]), int(second[p]), la, lo, rk)
+                if ji != (int(near[p, 0]), int(near[p, 1])):
+                    near[p] = ji
+                    redo.append(p)
+            changed = len(redo)
+            if redo:
+                redo = np.array(redo)
+                ok = near[redo, 0] >= 0
+                keep[redo] = 0
+                cell[redo] = 0
+                r = redo[ok]
+                if r.size:
+                    from .tracking import SurviveBatch
+                    alive = SurviveBatch(near[r], self._tmask_host, ic0.reshape(self.Nj, self.Ni)) == 0
+                    c2, found = self.find_containing_cell(SC[r], near[r])
+                    cell[r] = c2
+                    keep[r] = (alive & found).astype(np.int8)
+        if stats is not None:
+            stats.update(flagged=int(idx.size), changed=changed)
         return cell, near, keep
 
     def seed_locate_dev(self, SG_t, SC_t, ic0_t, stream=None):

@@ -11,6 +11,46 @@ __all__ = ['find_ji_of_min', 'NorthStereoProj', 'IsInsideQuadrangle', 'IsInsideQ
 from ._lib import as_c, check, hptr
 
 
+def _haversine_host(plat, plon, xlat, xlon):
+    """util.py:85-103 with numpy on the host, operation for operation: used only to re-decide the handful of seeds
+    whose nearest point or acceptance the device decided by less than 1e-11 relative -- numpy's
+    sin/cos/asin are the reference's own, CUDA's differ from them in the last ulp."""
+    to_rad = np.pi / 180.
+    R = 6360.
+    a1 = np.sin(0.5 * ((xlat - plat) * to_rad))
+    a2 = np.sin(0.5 * ((xlon - plon) * to_rad))
+    a3 = np.cos(xlat * to_rad) * np.cos(plat * to_rad)
+    return 2. * R * np.arcsin(np.sqrt(a1 * a1 + a3 * a2 * a2))
+
+
+def _recheck_nearest(pnt, k1, k2, latT, lonT, resKM, rd_found_km=2.5, max_itr=10):
+    """NearestPoint (locate.py:222-276) for ONE seed restricted to the device's two candidates (flat indices k1 and,
+    when the argmin was a near-tie, k2): first-minimum argmin in flat order like numpy's, then the reference's
+    acceptance ladder.  -> (jy, jx) or (-1, -1)."""
+    if k1 < 0:
+        return (-1, -1)
+    Ni = latT.shape[1]
+    cand = sorted(k for k in (k1, k2) if k >= 0)
+    lat, lon = latT.reshape(-1)[cand], lonT.reshape(-1)[cand]
+    d = _haversine_host(pnt[0], pnt[1], lat, lon)
+    kk = int(np.argmin(d))                                     # ties: the lower flat index, as np.argmin over the grid
+    k, dmin = cand[kk], d[kk]
+    jy, jx = k // Ni, k % Ni
+    rfnd, igo, lfound = rd_found_km, 0, False
+    while (not lfound) and igo < max_itr:                      # :250-269, no `ji_prv` box
+        igo = igo + 1
+        if igo == 1 and resKM is not None:
+            rfnd = 0.5 * resKM[jy, jx]                         # :262
+        if igo == 1:
+            igo = 2                                            # :264
+        lfound = bool(dmin < rfnd)                             # :266
+        if igo > 1 and not lfound:
+            rfnd = 1.2 * rfnd                                  # :268
+    if igo == max_itr:                                         # :274 a hit on the last pass is thrown away
+        return (-1, -1)
+    return (jy, jx) if lfound else (-1, -1)
+
+
 def find_ji_of_min(x):
     """locate.py:13-20 -- (j,i) of the first minimum of a 2-D array (host index arithmetic)."""
     k = int(np.argmin(x))

@@ -163,3 +163,74 @@ def test_cli_optional_physics_flags(tmp_path, monkeypatch):
     assert both.mean() > 0.8
     d = np.hypot(a["y_pos"][-1][both] - b["y_pos"][-1][both], a["x_pos"][-1][both] - b["x_pos"][-1][both])
     assert 0.0 < d.max() < 5.0 and np.median(d) < 1.0            # km
+
+
+@pytest.mark.gpu
+def test_cli_without_F_per_buoy_time_windows(tmp_path, monkeypatch):
+    """The default mode of the reference (no -F, `lUse2DTime`): every buoy has its own first and last model record,
+    derived from the seed file's 2-D `time_pos` (si3_part_tracker.py:264-312).  The seed file is built so that the
+    windows are known by construction; the `tracking12` file (the only one written in this mode, :546-571) must hold
+    each buoy's seed at its first record and the oracle's position after its last one."""
+    import si3_part_tracker as cli
+    from make_synth_case import write_case
+    from oracle import corc
+    import sitrack_b200 as sit
+    from synth.records import T0_EPOCH
+    nrec = 24
+    r = write_case(str(tmp_path / "in"), grid="small", nrec=nrec, hss=3)
+    z = dict(np.load(r["seed"]))
+    # the reference stops with an ERROR when SeedInit drops a buoy in this mode (its `zTpos = zTpos[:,idxK]` is
+    # commented out, si3_part_tracker.py:250,269-272) and so does the drop-in: seed only buoys that will be kept
+    kmaskt, latT, lonT, Yt, Xt, Yf, Xf, ResKM = quiet(sit.GetModelGrid, r["mesh"])
+    zt, zid, XG, XC = quiet(sit.LoadNCdata, r["seed"], krec=0)
+    ok = quiet(sit.SeedInit, zid, XG, XC, latT, lonT, Yf, Xf, ResKM, kmaskt,
+               xIceConc=np.asarray(r["records"][2][2], np.float64))[6]
+    assert 0 < ok.size < zid.size
+    z["id_buoy"] = z["id_buoy"][ok]
+    for k in ("latitude", "longitude", "y_pos", "x_pos"):
+        z[k] = z[k][:, ok]
+    nP = z["id_buoy"].size
+    rng = np.random.default_rng(5)
+    tm = T0_EPOCH + 1800 + 3600 * np.arange(nrec)                      # model time axis (record centres)
+    first = rng.integers(2, 7, nP); first[0] = 2                       # some buoy starts at the earliest record
+    last = rng.integers(14, 21, nP); last[1] = 20
+    tpos = np.stack([tm[first] - 1799, tm[last]]).astype("i4")         # see the docstring of record_windows' reference lines
+    z["time"] = np.array([tpos[0].min(), tpos[1].max()], "i4")
+    for k in ("latitude", "longitude", "y_pos", "x_pos"):
+        z[k] = np.concatenate([z[k], z[k]], axis=0)
+    z["time_pos"] = tpos
+    os.remove(r["seed"])
+    np.savez(r["seed"], **z)
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(sys, "argv", ["si3_part_tracker.py", "-i", r["si3"], "-m", r["mesh"], "-s", r["seed"],
+                                      "-N", "SYNTH4"])
+    quiet(cli.main)
+    out = os.listdir(tmp_path / "nc")
+    assert len(out) == 1 and "_tracking12_" in out[0], out           # no full-series file without -F
+    t12 = np.load(tmp_path / "nc" / out[0])
+    cache = np.load(tmp_path / "seed" / "Initialized_buoys_sitrack_seeding_nemoTsi3_19961215_00_HSS3_SYNTH4.npz")
+    keep = cache["idxKeep"]
+    assert keep.size == nP
+    # the windows the CLI must have used: kstrt from the time-span logic, per-buoy records by construction
+    idA = int(np.floor(tpos[0].min() / 3600.) * 3600); idB = int(np.ceil(tpos[1].max() / 3600.) * 3600)
+    Nt, kstrt, kstop, iTmA, iTmB = quiet(sit.GetTimeSpan, 3600, tm, idA, int(tm.min()), int(tm.max()), iStop=idB)
+    f_k, l_k = first[keep], last[keep]
+    assert f_k.min() >= kstrt and l_k.max() <= kstop
+    Yv, Xv, Yu, Xu = quiet(sit.GetModelUVGrid, r["mesh"])
+    g = dict(Yf=Yf, Xf=Xf, Yu=Yu, Xu=Xu, Yv=Yv, Xv=Xv, tmask=kmaskt)
+    U, V, IC = r["records"]
+    ref = corc.track(g, U[kstrt:kstop + 1], V[kstrt:kstop + 1], IC[kstrt:kstop + 1], cache["xPosC0"],
+                     cache["vJIt"].astype(np.int64), kstrt=kstrt, rec_first=f_k, rec_last=l_k)
+    b = np.arange(f_k.size)
+    k0, kN = f_k - kstrt, l_k - kstrt + 1
+    assert np.array_equal(t12["y_pos"][0], ref["posC"][k0, b, 0].astype("f4"))
+    assert np.array_equal(t12["x_pos"][0], ref["posC"][k0, b, 1].astype("f4"))
+    assert np.array_equal(t12["y_pos"][1], ref["posC"][kN, b, 0].astype("f4"))
+    assert np.array_equal(t12["x_pos"][1], ref["posC"][kN, b, 1].astype("f4"))
+    assert np.array_equal(t12["mask"][0], ref["mask"][k0, b]) and np.array_equal(t12["mask"][1], ref["mask"][kN, b])
+    assert t12["mask"][0].all() and 0 < t12["mask"][1].sum()
+    # per-buoy times (:334-340, :463): start of the first record, end of the last one (fill when discontinued)
+    assert np.array_equal(t12["time_pos"][0], tm[f_k] - 1800)
+    alive_end = t12["mask"][1] == 1
+    assert np.array_equal(t12["time_pos"][1][alive_end], (tm[l_k] + 1800)[alive_end])
+    assert (t12["time_pos"][1][~alive_end] == -9999).all()

@@ -650,3 +650,116 @@ def test_fast_projection_all_latitudes(sit, corc):
     near_pole = np.hypot(yx[:, 0], yx[:, 1]) < 1e-6
     assert dlon[~near_pole].max() < LATLON_TOL_DEG
     assert ll[-6, 0] == 90.0 and ll[-6, 1] == -45.0                                     # the pole: lam = lon0 like PROJ
+
+
+def test_config3_end_to_end_vs_oracle(torch, corc):
+    """BASELINE config 3 as a config: NANUK4-shaped grid, dense HSS1 seeding (~25 k buoys) plus 1000 SIDFEX-style
+    scattered seeds (some on land / outside the domain) -> SeedInit -> 24 hourly records, against the C oracle:
+    kept seeds, nearest points and host cells identical, then cells / alive flags / f8 positions bit-exact."""
+    import synth
+    import sitrack_b200 as sit
+    g = synth.make_grid(**synth.GRID_PRESETS["nanuk4"], seed=0)
+    nrec = 24
+    U, V, IC = synth.make_records(g, nrec, seed=1)
+    i1, G1, C1 = synth.hss_seeds(g, IC[0], khss=1)
+    i2, G2, C2 = synth.scattered_seeds(g, 1000, seed=2)
+    ids, SG, SC = np.concatenate([i1, i2 + i1.size]), np.concatenate([G1, G2]), np.concatenate([C1, C2])
+    assert 20_000 < i1.size < 100_000                               # every ocean T-point under ice, lat >= 55
+    jiT_o, keep_o, near_o = corc.seed_init(SG, SC, g["latT"], g["lonT"], g["Yf"], g["Xf"], g["ResKM"], g["tmask"], IC[0])
+    nPk, SGk, SCk, IDk, jiT, VRT, iKeep = sit.SeedInit(ids, SG, SC, g["latT"], g["lonT"], g["Yf"], g["Xf"], g["ResKM"],
+                                                        g["tmask"], xIceConc=IC[0].astype(np.float64))
+    ik_o = np.flatnonzero(keep_o)
+    assert np.array_equal(iKeep, ik_o) and np.array_equal(jiT, jiT_o[ik_o])
+    assert 0 < (keep_o[i1.size:] == 0).sum() < 1000                   # scattered seeds do get dropped, not all of them
+    ref = corc.track(g, U, V, IC, SCk, jiT.astype(np.int64))
+    with engine_for(g) as eng:
+        eng.set_buoys(SCk, jiT)
+        r = eng.track((U, V, IC), nrec, pos0=SCk)
+        p, c, a = eng.get_state()
+    assert np.array_equal(r["posC"], ref["posC"]) and np.array_equal(r["mask"], ref["mask"])
+    assert np.array_equal(r["n_alive"], ref["nalive"])
+    assert np.array_equal(c, ref["jiT"]) and np.array_equal(a, ref["alive"])
+    assert np.abs(r["posG"][1:] - ref["posG"][1:]).max() < 1e-9
+
+
+def test_seeding_subsample_on_the_twelfth_degree_grid(torch, corc):
+    """Seeding at 1/12 degree against the reference's whole-grid search (the oracle scans all 2.5 M T-points per
+    seed): 1500 seeds of the cfg4/cfg5 cloud + 500 scattered ones; nearest point, keep mask and host cell equal."""
+    import synth
+    g = synth.make_grid(**synth.GRID_PRESETS["arctic12"], seed=0)
+    U, V, IC = synth.make_records(g, 1, seed=1)
+    ids, SG, SC = synth.dense_seeds(g, 200_000, IC[0], seed=3)
+    sel = np.sort(np.random.default_rng(4).choice(SC.shape[0], 1500, replace=False))
+    i2, G2, C2 = synth.scattered_seeds(g, 500, seed=9)
+    SG, SC = np.concatenate([SG[sel], G2]), np.concatenate([SC[sel], C2])
+    jiT_o, keep_o, near_o = corc.seed_init(SG, SC, g["latT"], g["lonT"], g["Yf"], g["Xf"], g["ResKM"], g["tmask"], IC[0])
+    with engine_for(g) as eng:
+        eng.set_locate_grid(g["latT"], g["lonT"], g["ResKM"])
+        cell, near, keep = eng.seed_locate(SG, SC, IC[0])
+    assert np.array_equal(near, near_o) and np.array_equal(keep, keep_o)
+    ik = np.flatnonzero(keep)
+    assert np.array_equal(cell[ik], jiT_o[ik]) and ik.size > 1500
+
+
+def test_seed_locate_near_ties_are_rechecked_on_the_host(torch):
+    """Seeds placed (by bisection with numpy's Haversine) where two T-points are equidistant to ~1e-15, and seeds at
+    the acceptance radius 0.5 res 1.2^7 to ~1e-15: the device flags them and the host decides them with numpy, the
+    reference's own arithmetic (locate.py:253-266, util.py:85-103).  The final nearest points must equal numpy's
+    first-minimum argmin / acceptance over the neighbourhood, whichever way the device's last ulp fell."""
+    import synth
+    from sitrack_b200.locate import _haversine_host
+    g = synth.make_grid(**synth.GRID_PRESETS["small"], seed=0)
+    U, V, IC = synth.make_records(g, 1, seed=1)
+    la, lo, res = g["latT"], g["lonT"], g["ResKM"]
+    rng = np.random.default_rng(3)
+    SG = []
+    for t in range(300):                                         # argmin near-ties between T[j,i] and T[j,i+1]
+        j = rng.integers(5, g["Nj"] - 6); i = rng.integers(5, g["Ni"] - 6)
+        a, b = np.array([la[j, i], lo[j, i]]), np.array([la[j, i + 1], lo[j, i + 1]])
+        if abs(a[1] - b[1]) > 90:
+            continue
+        x0, x1 = 0.3, 0.7
+        f = lambda x: (lambda p: float(_haversine_host(p[0], p[1], a[0], a[1]) - _haversine_host(p[0], p[1], b[0], b[1])))(a + x * (b - a))
+        if f(x0) * f(x1) > 0:
+            continue
+        for _ in range(80):
+            xm = 0.5 * (x0 + x1)
+            if f(x0) * f(xm) <= 0: x1 = xm
+            else: x0 = xm
+        SG.append(a + x0 * (b - a))
+    n_tie = len(SG)
+    for t in range(200):                                         # acceptance near the limit: move away from a T-point of the first row
+        i = rng.integers(5, g["Ni"] - 6)
+        a = np.array([la[0, i], lo[0, i]]); inward = np.array([la[1, i], lo[1, i]])
+        r_lim = 0.5 * res[0, i]
+        for _ in range(7):
+            r_lim = 1.2 * r_lim
+        dirn = a - inward                                        # outward, in (lat,lon) degrees
+        x0, x1 = 0.0, 6.0
+        f = lambda x: float(_haversine_host(a[0] + x * dirn[0], a[1] + x * dirn[1], a[0], a[1]) - r_lim)
+        if f(x1) < 0:
+            continue
+        for _ in range(80):
+            xm = 0.5 * (x0 + x1)
+            if f(xm) <= 0: x0 = xm
+            else: x1 = xm
+        SG.append(a + (x0 if t % 2 else x1) * dirn)
+    SG = np.array(SG)
+    SG[:, 1] = np.mod(SG[:, 1], 360.0)
+    SC = np.zeros_like(SG)                                        # containing cell not under test here
+    with engine_for(g) as eng:
+        eng.set_locate_grid(la, lo, res)
+        st = {}
+        cell, near, keep = eng.seed_locate(SG, SC, IC[0], stats=st)
+        cell0, near0, keep0 = eng.seed_locate(SG, SC, IC[0], recheck=False)
+    assert st["flagged"] >= 0.8 * SG.shape[0], st                 # the constructed seeds are recognised as undecidable
+    # numpy's answer: first-minimum argmin over the whole grid, then the reference's ladder
+    for p in range(SG.shape[0]):
+        d = _haversine_host(SG[p, 0], SG[p, 1], la, lo)
+        k = int(np.argmin(d)); jy, jx = divmod(k, la.shape[1])
+        rf = 0.5 * res[jy, jx]
+        for _ in range(7):
+            rf = 1.2 * rf
+        want = (jy, jx) if d[jy, jx] < rf else (-1, -1)
+        assert (int(near[p, 0]), int(near[p, 1])) == want, (p, near[p], near0[p], want)
+    assert n_tie > 100

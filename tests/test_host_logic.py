@@ -136,3 +136,33 @@ def test_mesh_mask_with_levels_and_masked_time_pos(tmp_path, monkeypatch):
     assert int(np.min(t2d)) == 1000 and int(np.max(t2d)) == 4600
     first, last, name, batch, _ = ncio.SeedFileTimeInfo("a_b_c_d.nc", ltime2d=True)
     assert first == 0 and last == 7200                             # floor / ceil to the hour of 1000 .. 4600, not of -9999
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="upstream reference not present")
+def test_near_tie_recheck_is_the_reference_nearest_point():
+    """The host re-evaluation of flagged seeds (sitrack_b200/locate.py:_recheck_nearest, _haversine_host) against
+    the reference's NearestPoint / Haversine: same distances bit for bit, same (jy,jx) or (-1,-1), including seeds
+    at the acceptance limit 0.5 res 1.2^7 and beyond it."""
+    import synth
+    from sitrack_b200.locate import _recheck_nearest, _haversine_host
+    ref = ref_loader.load()
+    g = synth.make_grid(**synth.GRID_PRESETS["small"], seed=0)
+    rng = np.random.default_rng(0)
+    n_found = n_lost = 0
+    for t in range(200):
+        j = rng.integers(2, g["Nj"] - 3); i = rng.integers(2, g["Ni"] - 3)
+        sc = rng.choice([0.3, 1.0, 1.75, 1.79, 1.8, 2.5])
+        lat = g["latT"][j, i] + sc * 0.05 * rng.normal(); lon = g["lonT"][j, i] + sc * 0.2 * rng.normal()
+        if t % 2:                                                   # outside the grid, 1.5 .. 3 cells beyond its first row
+            x = rng.choice([1.5, 1.75, 1.79, 1.8, 2.0, 3.0])
+            lat = g["latT"][0, i] + x * (g["latT"][0, i] - g["latT"][1, i])
+            lon = g["lonT"][0, i] + x * (g["lonT"][0, i] - g["lonT"][1, i])
+        want = quiet(ref.NearestPoint, (lat, lon), g["latT"], g["lonT"], rd_found_km=2.5, resolkm=g["ResKM"], max_itr=10)
+        d = ref.Haversine(lat, lon, g["latT"], g["lonT"])
+        assert np.array_equal(_haversine_host(lat, lon, g["latT"], g["lonT"]), d)
+        k = int(np.argmin(d))
+        d2 = d.copy().reshape(-1); d2[k] = np.inf
+        got = _recheck_nearest((lat, lon), k, int(np.argmin(d2)), g["latT"], g["lonT"], g["ResKM"])
+        assert tuple(int(x) for x in want) == got
+        n_found += got[0] >= 0; n_lost += got[0] < 0
+    assert n_found > 20 and n_lost > 10

@@ -116,7 +116,7 @@ def test_projection_roundtrip_and_series(corc):
     assert np.abs(back - yx).max() < 1e-6
 
 
-@pytest.mark.parametrize("name", ["uv1", "uv0", "win"])
+@pytest.mark.parametrize("name", ["uv1", "uv0", "fast", "win"])
 def test_pyport_track_cases(gold_track, name):
     """The pure-Python port (timed as the as-shipped CPU baseline) is pinned by the same fixtures."""
     from oracle import pyport
@@ -125,7 +125,8 @@ def test_pyport_track_cases(gold_track, name):
     kw = dict(uv_strategy=c["uv_strategy"], kstrt=c["kstrt"])
     if c["win"]:
         kw.update(rec_first=T["win_first"], rec_last=T["win_last"])
-    posC, mask, jiT, alive, nsteps = pyport.track(g, T["U"], T["V"], T["IC"], T["pos0"], T["jiT0"], **kw)
+    sc = np.float32(c["scale"])
+    posC, mask, jiT, alive, nsteps = pyport.track(g, T["U"] * sc, T["V"] * sc, T["IC"], T["pos0"], T["jiT0"], **kw)
     assert np.array_equal(posC, T[name + "_posC"]) and np.array_equal(mask, T[name + "_mask"])
     assert np.array_equal(jiT, T[name + "_jiT"][-1]) and np.array_equal(alive, T[name + "_alive"][-1])
     assert nsteps == int(T[name + "_mask"][1:].sum()) - (int((T["win_first"] > c["kstrt"]).sum()) if c["win"] else 0)
