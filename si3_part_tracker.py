@@ -48,6 +48,9 @@ def __argument_parsing__():
     parser.add_argument('--interp', default='pick', choices=['pick', 'linear'],
                         help='velocity at the buoy: pick = upstream face pick (default); linear = C-grid linear (st_step_ext)')
     parser.add_argument('--hops', type=int, default=1, help='cell boundaries a buoy may cross per record (upstream: 1)')
+    parser.add_argument('--sort', action="store_true",
+                        help='store and write the buoys in cell-major order (much faster gathers on large clouds); the '
+                             'output files then list the buoys, with their IDs, in that order instead of seed order')
     parser.add_argument('--rows', default='f4', choices=['f4', 'f8'],
                         help='dtype of the trajectory rows copied off the GPU: f4 = the dtype the output files store (default), f8 = full in-memory arrays as upstream')
     args = parser.parse_args()
@@ -182,6 +185,13 @@ def main():
     z1st = zLst = None
     if lUse2DTime:
         z1st, zLst = record_windows(zTpos, nP, kstrt, kstop, ztime_model, iTmA, iTmB)
+    if args.sort and nP > 1:
+        # cell-major order for everything downstream: state, rows and the files (IDs carried along)
+        perm = np.argsort(vJIt[:, 0].astype(np.int64) * Ni + vJIt[:, 1], kind='stable')
+        xPosG0, xPosC0, IDs, vJIt = xPosG0[perm], xPosC0[perm], IDs[perm], vJIt[perm]
+        if z1st is not None:
+            z1st, zLst = z1st[perm], zLst[perm]
+        print(' *** --sort: buoys re-ordered by host cell (cell-major); the output files follow that order')
     lo, hi = 0, nP
     if world > 1:
         from sitrack_b200.dist import my_shard
@@ -202,6 +212,39 @@ def main():
               '(model:' + e2c(int(ztime_model[jrec])) + ')')
         return vU[jrec, :, :], vV[jrec, :, :], vIC[jrec, :, :]
 
+    def hstr(it):
+        c = split(':', e2c(it))[0]
+        return c.replace('-', '').replace('_', 'h')
+    corgn = 'NEMO-SI3_' + ModConf + '_' + ModExp
+    ext = '.npz' if str(cf_uv).endswith('.npz') else '.nc'
+
+    # Trajectory rows are written as they leave the GPU: the reference holds (Nt+1, nP, 2) arrays for the whole run
+    # (:326-328), here only the two rows the `tracking12` file needs stay in memory.
+    writer = None
+    if rank == 0 and not lUse2DTime:
+        cf_nc_out = './nc/' + corgn + '_tracking_' + SeedBatch + cdtbin + '_' + hstr(vTime[0]) + '_' + hstr(vTime[Nt]) + csfkm + ext
+        writer = sit.CloudBuoyWriter(cf_nc_out, Nt + 1, IDs, with_mask=True, corigin=corgn)
+        writer.write(0, vTime[0], xPosC0[:, 0], xPosC0[:, 1], xPosG0[:, 0], xPosG0[:, 1], mask=np.ones(nP, 'i1'))
+    z2XY, z2GC, zMSK = np.zeros((2, nP, 2)), np.zeros((2, nP, 2)), np.zeros((2, nP), dtype='i1')
+    z2XY[0], z2GC[0], zMSK[0] = xPosC0, xPosG0, 1                # each buoy's first row is its seed (:335-340)
+    kN = (zLst - kstrt + 1) if lUse2DTime else np.zeros(nP, dtype=int) + Nt      # row that closes each buoy's window
+
+    def keep_row(k, yx, ll, m):
+        """rank 0, whole rows in file order: append to the full-series file, remember the closing rows"""
+        if writer is not None:
+            writer.write(k + 1, vTime[k + 1], yx[:, 0], yx[:, 1], ll[:, 0], ll[:, 1], mask=m)
+        sel = np.flatnonzero(kN == k + 1)
+        z2XY[1, sel], z2GC[1, sel], zMSK[1, sel] = yx[sel], ll[sel], m[sel]
+
+    def sink(k, yx, ll, m):
+        if world == 1:
+            keep_row(k, yx, ll, m)
+        else:                                                     # one small gather per record, rank 0 writes
+            parts = [None] * world if rank == 0 else None
+            dist.gather_object((yx.copy(), ll.copy(), m.copy()), parts, dst=0)
+            if rank == 0:
+                keep_row(k, *[np.concatenate([p[i] for p in parts]) for i in range(3)])
+
     eng = sit.TrackEngine(xYf, xXf, xYu, xXu, xYv, xXv, tmask=imaskt, uv_strategy=args.uvstrategy, rdt=rdt,
                           rmin_conc=sit.rmin_conc, device=sit.config.device)
     eng.set_buoys(xPosC0[sh], vJIt[sh], cut(z1st), cut(zLst))
@@ -210,50 +253,33 @@ def main():
     if args.scheme != 'euler' or args.interp != 'pick' or args.hops != 1:
         physics = dict(scheme={'euler': 1, 'rk2': 2, 'rk4': 4}[args.scheme], interp=int(args.interp == 'linear'), max_hops=args.hops)
         print(' *** NOTE: optional physics beyond upstream sitrack is ON:', physics)
-    res = eng.track(record, Nt, kstrt=kstrt, pos0=xPosC0[sh], posG0=xPosG0[sh], rec_first=cut(z1st),
+    res = eng.track(record, Nt, kstrt=kstrt, rec_first=cut(z1st), sink=sink,
                     row_dtype='f8' if physics else args.rows, physics=physics)
     eng.close()
     ds.close()
+    n_alive = res['n_alive']
     if world > 1:
-        parts = [None] * world if rank == 0 else None
-        dist.gather_object(res, parts, dst=0)
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(n_alive))
+        dist.all_reduce(t)
+        n_alive = t.numpy()
         dist.barrier()
         dist.destroy_process_group()
         if rank != 0:
             return 0
-        res = dict(posC=np.concatenate([p['posC'] for p in parts], axis=1),
-                   posG=np.concatenate([p['posG'] for p in parts], axis=1),
-                   mask=np.concatenate([p['mask'] for p in parts], axis=1),
-                   n_alive=np.sum([p['n_alive'] for p in parts], axis=0))
-    xPosC, xPosG, xmask = res['posC'], res['posG'], res['mask']
     for jt in range(Nt):
-        print('   *   record ' + str(jt + kstrt) + ': number of buoys alive = ' + str(int(res['n_alive'][jt])))
+        print('   *   record ' + str(jt + kstrt) + ': number of buoys alive = ' + str(int(n_alive[jt])))
 
     # ---- outputs (reference :498-571) ---------------------------------------------------------------
-    def hstr(it):
-        c = split(':', e2c(it))[0]
-        return c.replace('-', '').replace('_', 'h')
-    corgn = 'NEMO-SI3_' + ModConf + '_' + ModExp
-    ext = '.npz' if str(cf_uv).endswith('.npz') else '.nc'
-    if not lUse2DTime:
-        cf_nc_out = './nc/' + corgn + '_tracking_' + SeedBatch + cdtbin + '_' + hstr(vTime[0]) + '_' + hstr(vTime[Nt]) + csfkm + ext
-        sit.ncSaveCloudBuoys(cf_nc_out, vTime, IDs, xPosC[:, :, 0], xPosC[:, :, 1], xPosG[:, :, 0], xPosG[:, :, 1],
-                             mask=xmask, corigin=corgn)
-    z2XY, z2GC, zMSK = np.zeros((2, nP, 2)), np.zeros((2, nP, 2)), np.zeros((2, nP), dtype='i1')
+    if writer is not None:
+        writer.close()
     if lUse2DTime:
         # per-buoy first and last valid rows; xTime follows from the windows (reference :334-340, :463)
         zTim = np.zeros((2, nP), dtype=int)
-        for jb in range(nP):
-            k0 = z1st[jb] - kstrt
-            kN = zLst[jb] - kstrt + 1
-            z2XY[0, jb], z2GC[0, jb], zMSK[0, jb] = xPosC[k0, jb], xPosG[k0, jb], xmask[k0, jb]
-            z2XY[1, jb], z2GC[1, jb], zMSK[1, jb] = xPosC[kN, jb], xPosG[kN, jb], xmask[kN, jb]
-            zTim[0, jb] = ztime_model[z1st[jb]] - int(rdt / 2)
-            zTim[1, jb] = (vTime[kN - 1] + int(rdt)) if xmask[kN, jb] else sit.FillValue
+        zTim[0] = ztime_model[z1st] - int(rdt / 2)
+        zTim[1] = np.where(zMSK[1] == 1, vTime[kN - 1] + int(rdt), int(sit.FillValue))
         zvt = np.array([np.mean(zTim[0, :]), np.mean(zTim[1, :])])
     else:
-        z2XY[0], z2GC[0], zMSK[0] = xPosC[0], xPosG[0], xmask[0]
-        z2XY[1], z2GC[1], zMSK[1] = xPosC[Nt], xPosG[Nt], xmask[Nt]
         zTim = []
         zvt = np.array([vTime[0], vTime[Nt]])
     cf_nc_out = './nc/' + corgn + '_tracking12_' + SeedBatch + cdtbin + '_' + hstr(zvt[0]) + '_' + hstr(zvt[1]) + csfkm + ext

@@ -220,16 +220,40 @@ class TrackEngine:
         return cell, found.astype(bool)
 
     # -- state -------------------------------------------------------------------------
-    def set_buoys(self, pos, cell, rec_first=None, rec_last=None):
+    def set_buoys(self, pos, cell, rec_first=None, rec_last=None, sort=False):
+        """sort=True stores the buoys in cell-major order (stable sort by host cell): a warp's 32 buoys then sit in
+        neighbouring cells and its gathers touch a handful of lines instead of 32 (SURVEY section 7 "gather
+        locality"; the reference keeps seed order, sitrack/tracking.py:166-178).  The permutation is `self.perm`
+        (engine slot -> caller's index); track() in full-series mode and get_state() give results back in the
+        caller's order, a `sink` receives rows in engine order."""
         pos, cell = as_c(pos, np.float64), as_c(cell, np.int32)
         rf = None if rec_first is None else as_c(rec_first, np.int32)
         rl = None if rec_last is None else as_c(rec_last, np.int32)
+        self.perm = None
+        if sort and pos.shape[0] > 1:
+            perm = np.argsort(cell[:, 0].astype(np.int64) * self.Ni + cell[:, 1], kind="stable")
+            pos, cell = as_c(pos[perm], np.float64), as_c(cell[perm], np.int32)
+            rf = None if rf is None else as_c(rf[perm], np.int32)
+            rl = None if rl is None else as_c(rl[perm], np.int32)
+            self.perm = perm
         check(self.L.st_set_buoys(self.h, pos.shape[0], hptr(pos), hptr(cell), hptr(rf), hptr(rl)), self.h)
         self.nP = pos.shape[0]
 
-    def set_buoys_dev(self, pos_t, cell_t, rec_first_t=None, rec_last_t=None, stream=None):
+    def set_buoys_dev(self, pos_t, cell_t, rec_first_t=None, rec_last_t=None, stream=None, sort=False):
+        """Device tensors in.  sort=True: as set_buoys, the permutation stays on the device as `self.perm_t`."""
         torch = _torch()
         stream = stream or torch.cuda.current_stream(pos_t.device)
+        self.perm = None
+        self.perm_t = None
+        if sort and pos_t.shape[0] > 1:
+            with torch.cuda.stream(stream):
+                key = cell_t[:, 0].to(torch.int64) * self.Ni + cell_t[:, 1].to(torch.int64)
+                perm = torch.argsort(key, stable=True)
+                pos_t, cell_t = pos_t[perm].contiguous(), cell_t[perm].contiguous()
+                rec_first_t = None if rec_first_t is None else rec_first_t[perm].contiguous()
+                rec_last_t = None if rec_last_t is None else rec_last_t[perm].contiguous()
+            self.perm_t = perm
+            self._sorted_keepalive = (pos_t, cell_t, rec_first_t, rec_last_t)   # until the async copy below has run
         check(self.L.st_set_buoys_dev(self.h, pos_t.shape[0], _dptr(pos_t), _dptr(cell_t), _dptr(rec_first_t),
                                       _dptr(rec_last_t), _sptr(stream)), self.h)
         self.nP = pos_t.shape[0]
@@ -239,6 +263,12 @@ class TrackEngine:
         cell = np.zeros((self.nP, 2), np.int32)
         alive = np.zeros(self.nP, np.int8)
         check(self.L.st_get_state(self.h, hptr(pos), hptr(cell), hptr(alive)), self.h)
+        perm = getattr(self, "perm", None)
+        if perm is not None:                                     # back to the caller's order
+            out = [np.empty_like(a) for a in (pos, cell, alive)]
+            for o, a in zip(out, (pos, cell, alive)):
+                o[perm] = a
+            return tuple(out)
         return pos, cell, alive
 
     # -- records -----------------------------------------------------------------------
@@ -390,6 +420,9 @@ class TrackEngine:
         dev = torch.device("cuda", self.device)
         nP = self.nP
         get = _record_getter(records)
+        perm = getattr(self, "perm", None)
+        if perm is not None and chunk and chunk > 1 and sink is None:
+            raise ValueError("the chunked season path keeps the caller's order: use set_buoys(sort=False) with it")
         if row_dtype not in ("f8", "f4"):
             raise ValueError("row_dtype must be 'f8' or 'f4'")
         rdt = torch.float32 if row_dtype == "f4" else torch.float64
@@ -429,12 +462,23 @@ class TrackEngine:
                 y, l, m = rows(k)
                 sink(k, y.numpy(), None if l is None else l.numpy(), m.numpy())
 
-        for k in range(nrec):
+        # reader thread (SURVEY 8b "threading"): record k+1 is read and converted into its pinned staging slot while
+        # the main thread queues the GPU work of record k (netCDF4 reads and numpy copies release the GIL)
+        from concurrent.futures import ThreadPoolExecutor
+
+        def load(k):
             b = k % 2
             if k >= 2:
                 ev_in[k - 2].synchronize()                 # staging slot b has left the host
             u, v, ic = get(k)
             stg[b][0], stg[b][1], stg[b][2] = u, v, ic     # f4 copy into pinned memory
+        pool = ThreadPoolExecutor(1)
+        nxt = pool.submit(load, 0) if nrec > 0 else None
+        for k in range(nrec):
+            b = k % 2
+            nxt.result()
+            if k + 1 < nrec:
+                nxt = pool.submit(load, k + 1)             # waits for ev_in[k-1], recorded below before it can matter
             if k >= 2:
                 s_in.wait_event(ev_step[k - 2])            # device slot b no longer read
             self.submit_record(b, s_in)
@@ -464,10 +508,14 @@ class TrackEngine:
             else:
                 drain(k)
         torch.cuda.synchronize(dev)
+        pool.shutdown()
         n_alive = d_na.cpu().numpy()
         if not keep:
             return dict(n_alive=n_alive)
         posC, posG, mask = posC.numpy(), posG.numpy(), mask.numpy()
+        if perm is not None:                                # engine order -> the caller's order
+            inv = np.empty_like(perm); inv[perm] = np.arange(perm.size)
+            posC, posG, mask = posC[:, inv], posG[:, inv], mask[:, inv]
         if pos0 is not None:
             if rec_first is None:
                 posC[0] = pos0; mask[0] = 1

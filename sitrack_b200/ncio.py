@@ -21,7 +21,7 @@ from .util import epoch2clock as e2c
 
 __all__ = ["tunits_default", "FillValue", "GetModelGrid", "GetModelUVGrid", "GetSeedMask",
            "GetModelSeaIceConc", "ncSaveCloudBuoys", "LoadNCtime", "LoadNCdata", "SeedFileTimeInfo",
-           "ModelFileTimeInfo", "open_dataset"]
+           "ModelFileTimeInfo", "open_dataset", "CloudBuoyWriter"]
 
 tunits_default = 'seconds since 1970-01-01 00:00:00'     # ncio.py:15
 FillValue = -9999.                                       # ncio.py:19
@@ -150,62 +150,104 @@ _CLOUD_VARS = [
 ]
 
 
-def ncSaveCloudBuoys(cf_out, ptime, pIDs, pY, pX, pLat, pLon, mask=[], xtime=[],
-                     tunits=tunits_default, fillVal=FillValue, corigin=None):
-    """ncio.py:131-197: time i4, buoy i4, id_buoy i8, latitude/longitude/y_pos/x_pos f4 (time,buoy)
-    [+ mask i1, time_pos i4].  netCDF4 when available and the name does not end in .npz, otherwise an
-    .npz with the same variables and dtypes."""
-    print('\n *** [ncSaveCloudBuoys]: About to generate file: ' + cf_out + ' ...')
-    shp = (np.shape(ptime)[0], np.shape(pIDs)[0])
-    fields = dict(latitude=pLat, longitude=pLon, y_pos=pY, x_pos=pX)
-    if any(np.shape(a) != shp for a in fields.values()):
-        _die('ERROR [ncSaveCloudBuoys]: one of the 2D arrays has a wrong shape!!!')
-    extra = {}
-    if np.shape(mask) == shp:
-        extra['mask'] = ('i1', np.asarray(mask))
-    if np.shape(xtime) == shp:
-        extra['time_pos'] = ('i4', np.asarray(xtime))
-    nc = None
-    if not str(cf_out).endswith(".npz"):
-        try:
-            import netCDF4 as nc
-        except ImportError:
-            cf_out += ".npz"
-            print('      (netCDF4 not available: writing ' + cf_out + ' with the same variables)')
-    if nc is None:
-        out = dict(time=np.asarray(ptime).astype('i4'), buoy=np.arange(shp[1], dtype='i4'),
-                   id_buoy=np.asarray(pIDs).astype('i8'))
-        out.update({k: np.asarray(v, 'f4') for k, v in fields.items()})
-        out.update({k: v.astype(dt) for k, (dt, v) in extra.items()})
-        np.savez_compressed(cf_out, **out)
-    else:
-        with nc.Dataset(cf_out, 'w', format='NETCDF4') as f:
+class CloudBuoyWriter:
+    """Record-by-record writer of a cloud-of-buoys file: the variables, dtypes and attributes of ncSaveCloudBuoys
+    (reference ncio.py:131-197), one `write(jt, ...)` per trajectory row, so that a run never has to hold the
+    (Nt+1, nP, 2) series the reference allocates (si3_part_tracker.py:326-328; SURVEY section 5 "output volume").
+    netCDF4 when available and the name does not end in .npz (unlimited `time` dimension, rows appended as they
+    come); otherwise an .npz with the same variables, assembled from on-disk .npy members (numpy memmaps), never
+    from arrays in memory."""
+
+    def __init__(self, cf_out, ntime, pIDs, with_mask=False, with_time_pos=False, tunits=tunits_default,
+                 fillVal=FillValue, corigin=None):
+        print('\n *** [ncSaveCloudBuoys]: About to generate file: ' + cf_out + ' ...')
+        self.ntime, self.nP = int(ntime), int(np.shape(pIDs)[0])
+        self.names = [n for n, _, _ in _CLOUD_VARS] + (['mask'] if with_mask else []) + (['time_pos'] if with_time_pos else [])
+        self._dt = {n: dt for n, dt, _ in _CLOUD_VARS}
+        self._dt.update(mask='i1', time_pos='i4')
+        nc = None
+        if not str(cf_out).endswith(".npz"):
+            try:
+                import netCDF4 as nc
+            except ImportError:
+                cf_out += ".npz"
+                print('      (netCDF4 not available: writing ' + cf_out + ' with the same variables)')
+        self.cf_out, self._nc = cf_out, nc
+        if nc is None:
+            import tempfile
+            self._tmp = tempfile.mkdtemp(prefix=".cloud_", dir=os.path.dirname(os.path.abspath(cf_out)) or ".")
+            mm = lambda n, dt, shp: np.lib.format.open_memmap(os.path.join(self._tmp, n + ".npy"), mode='w+', dtype=dt, shape=shp)
+            self._v = {n: mm(n, self._dt[n], (self.ntime, self.nP)) for n in self.names}
+            self._v['time'] = mm('time', 'i4', (self.ntime,))
+            mm('buoy', 'i4', (self.nP,))[:] = np.arange(self.nP, dtype='i4')
+            mm('id_buoy', 'i8', (self.nP,))[:] = np.asarray(pIDs).astype('i8')
+        else:
+            f = self._f = nc.Dataset(cf_out, 'w', format='NETCDF4')
             f.createDimension('time', None)
-            f.createDimension('buoy', shp[1])
+            f.createDimension('buoy', self.nP)
             vt = f.createVariable('time', 'i4', ('time',)); vt.units = tunits
-            f.createVariable('buoy', 'i4', ('buoy',))[:] = np.arange(shp[1], dtype='i8')
+            f.createVariable('buoy', 'i4', ('buoy',))[:] = np.arange(self.nP, dtype='i8')
             vid = f.createVariable('id_buoy', 'i8', ('buoy',)); vid.units = 'ID of buoy'
-            vid[:] = pIDs[:]
+            vid[:] = np.asarray(pIDs)[:]
             zkw = dict(zlib=True, complevel=9)
-            handles = {}
+            self._v = {'time': vt}
             for name, dt, units in _CLOUD_VARS:
-                handles[name] = f.createVariable(name, dt, ('time', 'buoy'), fill_value=fillVal, **zkw)
-                handles[name].units = units
-            if 'mask' in extra:
-                handles['mask'] = f.createVariable('mask', 'i1', ('time', 'buoy'), **zkw)
-            if 'time_pos' in extra:
-                handles['time_pos'] = f.createVariable('time_pos', 'i4', ('time', 'buoy'), fill_value=fillVal, **zkw)
-                handles['time_pos'].units = tunits
-            sources = dict(fields, **{k: v for k, (_, v) in extra.items()})
-            for jt in range(shp[0]):
-                vt[jt] = ptime[jt]
-                for name, h in handles.items():
-                    h[jt, :] = sources[name][jt, :]
+                self._v[name] = f.createVariable(name, dt, ('time', 'buoy'), fill_value=fillVal, **zkw)
+                self._v[name].units = units
+            if with_mask:
+                self._v['mask'] = f.createVariable('mask', 'i1', ('time', 'buoy'), **zkw)
+            if with_time_pos:
+                self._v['time_pos'] = f.createVariable('time_pos', 'i4', ('time', 'buoy'), fill_value=fillVal, **zkw)
+                self._v['time_pos'].units = tunits
             if corigin:
                 f.Origin = corigin
             f.About = 'Lagrangian sea-ice drift'
             f.Author = 'Generated with `%s` of `sitrack` (L. Brodeau, 2023)' % os.path.basename(sys.argv[0])
-    print('      ===> ' + cf_out + ' saved!')
+
+    def write(self, jt, time, y, x, lat, lon, mask=None, time_pos=None):
+        """Row jt of every variable ((nP,) arrays, any float dtype: stored as f4 like the reference's file)."""
+        self._v['time'][jt] = time
+        row = dict(latitude=lat, longitude=lon, y_pos=y, x_pos=x, mask=mask, time_pos=time_pos)
+        for n in self.names:
+            self._v[n][jt, :] = np.asarray(row[n])
+
+    def close(self):
+        if self._nc is not None:
+            self._f.close()
+        else:
+            import shutil
+            import zipfile
+            for v in self._v.values():
+                v.flush()
+            self._v = {}
+            with zipfile.ZipFile(self.cf_out, 'w', zipfile.ZIP_DEFLATED, allowZip64=True) as z:
+                for fn in sorted(os.listdir(self._tmp)):
+                    z.write(os.path.join(self._tmp, fn), arcname=fn)         # streamed from disk, like np.savez's members
+            shutil.rmtree(self._tmp, ignore_errors=True)
+        print('      ===> ' + self.cf_out + ' saved!')
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def ncSaveCloudBuoys(cf_out, ptime, pIDs, pY, pX, pLat, pLon, mask=[], xtime=[],
+                     tunits=tunits_default, fillVal=FillValue, corigin=None):
+    """ncio.py:131-197: time i4, buoy i4, id_buoy i8, latitude/longitude/y_pos/x_pos f4 (time,buoy)
+    [+ mask i1, time_pos i4].  netCDF4 when available and the name does not end in .npz, otherwise an
+    .npz with the same variables and dtypes.  (Whole arrays in, like upstream; CloudBuoyWriter streams.)"""
+    shp = (np.shape(ptime)[0], np.shape(pIDs)[0])
+    fields = dict(latitude=pLat, longitude=pLon, y_pos=pY, x_pos=pX)
+    if any(np.shape(a) != shp for a in fields.values()):
+        _die('ERROR [ncSaveCloudBuoys]: one of the 2D arrays has a wrong shape!!!')
+    wm, wt = np.shape(mask) == shp, np.shape(xtime) == shp
+    with CloudBuoyWriter(cf_out, shp[0], pIDs, with_mask=wm, with_time_pos=wt, tunits=tunits, fillVal=fillVal,
+                         corigin=corigin) as w:
+        for jt in range(shp[0]):
+            w.write(jt, ptime[jt], pY[jt], pX[jt], pLat[jt], pLon[jt], mask=mask[jt] if wm else None,
+                    time_pos=xtime[jt] if wt else None)
     return 0
 
 

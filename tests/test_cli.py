@@ -234,3 +234,169 @@ def test_cli_without_F_per_buoy_time_windows(tmp_path, monkeypatch):
     alive_end = t12["mask"][1] == 1
     assert np.array_equal(t12["time_pos"][1][alive_end], (tm[l_k] + 1800)[alive_end])
     assert (t12["time_pos"][1][~alive_end] == -9999).all()
+
+
+class _FakeNC:
+    """A minimal in-memory stand-in for the netCDF4 module (absent from this image and from the GPU boxes), with the
+    calls the reference's I/O makes: Dataset(fn, 'w'|'r'), createDimension, createVariable(name, dtype, dims,
+    fill_value=, zlib=, complevel=), variable slicing / assignment with an unlimited first dimension, attributes."""
+    files = {}
+
+    class Var:
+        def __init__(self, dtype, shape, fill):
+            self.dtype, self.fill = np.dtype(dtype), fill
+            self.a = np.zeros([0 if s is None else s for s in shape], self.dtype)
+            self.shape0_unlimited = shape and shape[0] is None
+
+        def _grow(self, n):
+            if self.shape0_unlimited and n > self.a.shape[0]:
+                pad = np.full((n - self.a.shape[0],) + self.a.shape[1:], self.fill if self.fill is not None else 0, self.dtype)
+                self.a = np.concatenate([self.a, pad])
+
+        def __setitem__(self, k, v):
+            k0 = k[0] if isinstance(k, tuple) else k
+            if isinstance(k0, (int, np.integer)):
+                self._grow(int(k0) + 1)
+            elif isinstance(k0, slice) and k0 == slice(None) and self.shape0_unlimited:
+                self._grow(np.shape(v)[0])
+            self.a[k] = np.asarray(v).astype(self.dtype)         # like netCDF4: cast to the variable's type
+
+        def __getitem__(self, k):
+            return np.ma.masked_equal(self.a[k], self.fill) if self.fill is not None else self.a[k]
+
+        shape = property(lambda self: self.a.shape)
+
+    class Dim:
+        def __init__(self, ds, name):
+            self.ds, self.name = ds, name
+
+        @property
+        def size(self):
+            n = self.ds._dims[self.name]
+            if n is None:
+                return max([v.a.shape[0] for v in self.ds.variables.values() if v.shape0_unlimited] or [0])
+            return n
+
+    class Dataset:
+        def __init__(self, fn, mode='r', format=None):
+            if mode == 'w':
+                object.__setattr__(self, "_dims", {}); object.__setattr__(self, "variables", {})
+                object.__setattr__(self, "attrs", {}); _FakeNC.files[str(fn)] = self
+            else:
+                src = _FakeNC.files[str(fn)]
+                for k in ("_dims", "variables", "attrs"):
+                    object.__setattr__(self, k, getattr(src, k))
+            object.__setattr__(self, "dimensions", {n: _FakeNC.Dim(self, n) for n in self._dims})
+
+        def createDimension(self, name, size):
+            self._dims[name] = size
+            self.dimensions[name] = _FakeNC.Dim(self, name)
+
+        def createVariable(self, name, dtype, dims, fill_value=None, zlib=False, complevel=4):
+            assert all(d in self._dims for d in dims) and 0 <= complevel <= 9
+            v = _FakeNC.Var(dtype, [self._dims[d] for d in dims], fill_value)
+            self.variables[name] = v
+            return v
+
+        def __setattr__(self, k, v):
+            self.attrs[k] = v
+
+        def close(self):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *e):
+            pass
+
+
+def test_netcdf_branch_of_the_writer_and_readers(monkeypatch, tmp_path):
+    """The netCDF4 code paths of ncio (writer: ncio.py:131-197; readers: :199-326) executed against an in-memory
+    stand-in for the module: variables, dtypes, fill values, units and global attributes as the reference writes
+    them, rows appended one at a time through the unlimited time dimension, and read back through LoadNCdata."""
+    import types
+    import sitrack_b200 as sit
+    fake = types.ModuleType("netCDF4"); fake.Dataset = _FakeNC.Dataset
+    monkeypatch.setitem(sys.modules, "netCDF4", fake)
+    monkeypatch.setattr(sit.ncio, "chck4f", lambda fn: None)
+    nt, nP = 4, 7
+    rng = np.random.default_rng(0)
+    t = 850608000 + 3600 * np.arange(nt)
+    ids = np.arange(nP) + 11
+    Y, X = rng.uniform(-900, 900, (nt, nP)), rng.uniform(-900, 900, (nt, nP))
+    La, Lo = rng.uniform(60, 90, (nt, nP)), rng.uniform(-180, 180, (nt, nP))
+    M = (rng.random((nt, nP)) > 0.2).astype("i1")
+    Y[2, 3] = -9999.
+    f = str(tmp_path / "out.nc")
+    quiet(sit.ncSaveCloudBuoys, f, t, ids, Y, X, La, Lo, mask=M, corigin="NEMO-SI3_X_Y")
+    ds = _FakeNC.files[f]
+    assert sorted(ds.variables) == sorted(["time", "buoy", "id_buoy", "latitude", "longitude", "y_pos", "x_pos", "mask"])
+    assert ds.variables["y_pos"].dtype == np.float32 and ds.variables["time"].dtype == np.int32
+    assert ds.variables["id_buoy"].dtype == np.int64 and ds.variables["mask"].dtype == np.int8
+    assert ds.variables["time"].units == sit.tunits_default and ds.attrs["Origin"] == "NEMO-SI3_X_Y"
+    assert ds.variables["y_pos"].fill == -9999. and ds.dimensions["time"].size == nt
+    zt, ids2, LL, YX, msk = quiet(sit.LoadNCdata, f, krec=2, lmask=True)
+    assert zt == t[2] and np.array_equal(ids2, ids) and np.array_equal(msk, M[2])
+    assert np.array_equal(np.ma.filled(YX[:, 0], -9999.), Y[2].astype("f4").astype("f8"))
+    assert np.allclose(LL[:, 1], np.mod(Lo[2].astype("f4"), 360.))
+    # streaming: the same file row by row, with per-buoy times
+    f2 = str(tmp_path / "out2.nc")
+    tp = np.tile(t[:, None], (1, nP)).astype("i4")
+    with contextlib.redirect_stdout(io.StringIO()):
+        with sit.CloudBuoyWriter(f2, nt, ids, with_mask=True, with_time_pos=True) as w:
+            for jt in range(nt):
+                w.write(jt, t[jt], Y[jt], X[jt], La[jt], Lo[jt], mask=M[jt], time_pos=tp[jt])
+    d2 = _FakeNC.files[f2]
+    for n in ("latitude", "longitude", "y_pos", "x_pos", "mask", "time"):
+        assert np.array_equal(d2.variables[n].a, ds.variables[n].a), n
+    assert d2.variables["time_pos"].units == sit.tunits_default
+    Nt, t1d, t2d = quiet(sit.LoadNCtime, f2, ltime2d=True)
+    assert Nt == nt and np.array_equal(np.asarray(t2d), tp)
+
+
+@pytest.mark.gpu
+def test_cli_sort_flag_permutes_buoys_not_trajectories(tmp_path, monkeypatch):
+    """--sort stores and writes the buoys in cell-major order: the files list the same buoys (by ID) with the same
+    trajectories, bit for bit, in a different order; the engine-level form (set_buoys(sort=True)) hands results
+    back in the caller's order."""
+    import si3_part_tracker as cli
+    from make_synth_case import write_case
+    import sitrack_b200 as sit
+    r = write_case(str(tmp_path / "in"), grid="small", nrec=12, hss=2)
+    # shuffle the seed file so that seed order is far from cell order
+    z = dict(np.load(r["seed"]))
+    sh = np.random.default_rng(1).permutation(z["id_buoy"].size)
+    z["id_buoy"] = z["id_buoy"][sh]
+    for k in ("latitude", "longitude", "y_pos", "x_pos"):
+        z[k] = z[k][:, sh]
+    os.remove(r["seed"]); np.savez(r["seed"], **z)
+    outs = {}
+    for tag, extra in (("seed", []), ("sorted", ["--sort"])):
+        d = tmp_path / tag
+        d.mkdir(); monkeypatch.chdir(d)
+        monkeypatch.setattr(sys, "argv", ["si3_part_tracker.py", "-i", r["si3"], "-m", r["mesh"], "-s", r["seed"],
+                                          "-F", "-N", "SYNTH4"] + extra)
+        quiet(cli.main)
+        f = [f for f in os.listdir(d / "nc") if "_tracking_" in f]
+        outs[tag] = np.load(d / "nc" / f[0])
+    a, b = outs["seed"], outs["sorted"]
+    assert not np.array_equal(a["id_buoy"], b["id_buoy"]) and sorted(a["id_buoy"]) == sorted(b["id_buoy"])
+    ia, ib = np.argsort(a["id_buoy"]), np.argsort(b["id_buoy"])
+    for k in ("y_pos", "x_pos", "latitude", "longitude", "mask"):
+        assert np.array_equal(a[k][:, ia], b[k][:, ib]), k
+    # engine level: sorted storage, caller's order out
+    cache = np.load(tmp_path / "seed" / "seed" / os.listdir(tmp_path / "seed" / "seed")[0])
+    kmaskt, latT, lonT, Yt, Xt, Yf, Xf, ResKM = quiet(sit.GetModelGrid, r["mesh"])
+    Yv, Xv, Yu, Xu = quiet(sit.GetModelUVGrid, r["mesh"])
+    U, V, IC = r["records"]
+    res = {}
+    for srt in (False, True):
+        with sit.TrackEngine(Yf, Xf, Yu, Xu, Yv, Xv, tmask=kmaskt) as eng:
+            eng.set_buoys(cache["xPosC0"], cache["vJIt"], sort=srt)
+            assert (eng.perm is not None) == srt
+            res[srt] = (eng.track((U, V, IC), 12, pos0=cache["xPosC0"]), eng.get_state())
+    for k in ("posC", "posG", "mask", "n_alive"):
+        assert np.array_equal(res[False][0][k], res[True][0][k]), k
+    for x, y in zip(res[False][1], res[True][1]):
+        assert np.array_equal(x, y)
