@@ -177,7 +177,13 @@ def run_ours(args):
 
     K, W = args.steps, args.warmup
     wl = WORKLOADS[args.workload]
-    g, (U, V, IC), SG, SC = build_workload(args.workload, rank)
+    strong = args.scaling == "strong"
+    n_dense = None
+    if strong:
+        if wl["kind"] != "dense":
+            raise SystemExit("--scaling strong needs a dense workload (cfg4, cfg5)")
+        n_dense = wl["buoys"] // world                    # the workload's buoys are the TOTAL, sharded over the ranks
+    g, (U, V, IC), SG, SC = build_workload(args.workload, rank, n_dense=n_dense)
     Nj, Ni = g["Nj"], g["Ni"]
     R = U.shape[0]
     eng = sit.TrackEngine(g["Yf"], g["Xf"], g["Yu"], g["Xu"], g["Yv"], g["Xv"], tmask=g["tmask"], device=local)
@@ -204,6 +210,14 @@ def run_ours(args):
     kp = keep_t.bool()
     pos0_t, cell0_t = SC_t[kp].contiguous(), cell_t[kp].contiguous()
     nP = int(pos0_t.shape[0])
+    if not args.no_shuffle:
+        # the synthetic generator emits the cloud cell by cell; hand it to the product in RANDOM order, so that the
+        # gather locality of the step comes from the product (set_buoys(sort=True): cell-major storage) and not from
+        # the way the input happened to be generated
+        gen = torch.Generator(device=dev); gen.manual_seed(11 + rank)
+        shuf = torch.randperm(nP, device=dev, generator=gen)
+        pos0_t, cell0_t = pos0_t[shuf].contiguous(), cell0_t[shuf].contiguous()
+        del shuf
     log("[rank %d] seeding: %d of %d seeds kept, k_seed_locate %.2f ms (%.3g buoys/s)"
         % (rank, nP, SC_t.shape[0], seed_ms, SC_t.shape[0] / (seed_ms * 1e-3)))
     del SG_t, near_t, keep_t, cell_t
@@ -222,8 +236,8 @@ def run_ours(args):
     o_mk = [torch.empty((nP,), dtype=torch.int8, device=dev) for _ in range(NB)]
     stream = torch.cuda.Stream(dev)
 
-    def reset():
-        eng.set_buoys_dev(pos0_t, cell0_t, stream=stream)
+    def reset(sort=True):
+        eng.set_buoys_dev(pos0_t, cell0_t, stream=stream, sort=sort and not args.no_shuffle)
 
     def barrier():
         torch.cuda.synchronize()
@@ -234,9 +248,9 @@ def run_ours(args):
     def ll_of(b):                    # --no-latlon: diagnostic run without the lat/lon row (not a bench value)
         return None if args.no_latlon else o_ll[b]
 
-    def timed_steps(nsteps, nwarm, after_step=None):
+    def timed_steps(nsteps, nwarm, after_step=None, sort=True):
         """-> (ms, alive buoy-steps in the timed part).  after_step(k, buf) may enqueue extra work."""
-        reset()
+        reset(sort)
         na = torch.zeros((nwarm + nsteps,), dtype=torch.int64, device=dev)
         for k in range(nwarm):
             b = k % NB
@@ -285,8 +299,18 @@ def run_ours(args):
             "buoy_steps_per_launch": bsteps / K, "us_per_launch": round(ms / K * 1e3, 2)}
 
     extra = {}
+    # -- what the product's cell-major storage buys: the same shuffled input stored as it came ----------------
+    if not args.no_shuffle and nP > 100_000:
+        Ku = max(3, min(K, 20))
+        ms_u, bs_u = timed_steps(Ku, 3, sort=False)
+        ms_u, bs_u = reduce_max_sum(ms_u, bs_u)
+        extra["input_order"] = {"what": "the seeds reach the product in random order; value/roofline: stored cell-major by "
+                                        "set_buoys(sort=True) (stable sort by host cell, once per run); here: the same input "
+                                        "stored in the order it came (sort=False)",
+                                "us_per_launch_sorted_by_product": round(ms_max / K * 1e3, 2),
+                                "us_per_launch_unsorted": round(ms_u / Ku * 1e3, 2), "steps_unsorted": Ku}
     # -- small clouds: the season path, R resident records per launch of k_advect_multi -----------
-    if wl["grid"] == "nanuk4" or args.multi:
+    if wl["grid"] == "nanuk4" or args.multi or (strong and nP < 2_000_000):
         Rm = args.multi or R
         rec_t = torch.from_numpy(np.stack([U, V, IC], axis=1).astype(np.float32)).to(dev).contiguous()[:Rm]
         m_yx = torch.empty((Rm, nP, 2), dtype=torch.float64, device=dev)
@@ -344,17 +368,23 @@ def run_ours(args):
         dist.all_reduce(cnt)
         cnts = cnt.cpu().numpy()
         offs = np.concatenate([[0], np.cumsum(cnts)])
-        for tag, f4 in (("allgather_fused", False), ("allgather_fused_f4", True)):
+        # every rank's block starts on a tile boundary of the gathered array (the bulk form needs 16-byte aligned tiles)
+        offs = np.concatenate([[0], np.cumsum((cnts + 31) // 32 * 32)])
+        checks = {}
+        forms = (("allgather_fused", False, 0), ("allgather_fused_f4", True, 0), ("allgather_bulk_f4", True, 2),
+                 ("allgather_dma_f4", True, 1), ("allgather_bulk", False, 2))
+        for tag, f4, mode in forms:
             reset(); torch.cuda.synchronize()
             hnd = eng.gather_create(rank, world, int(offs[-1]), int(offs[rank]), f4=f4, nbuf=NB)
             mine = torch.tensor(list(hnd), dtype=torch.uint8, device=dev)
             allh = torch.empty((world * 64,), dtype=torch.uint8, device=dev)
             dist.all_gather_into_tensor(allh, mine)
             eng.gather_connect_ipc(bytes(allh.cpu().numpy().tobytes()))
+            eng.gather_set_mode(mode)
             barrier()
             cons = torch.cuda.Stream(dev)
             Ka = max(4, min(K, 200)); Wa = min(W, 5)
-            na_g = torch.zeros((Wa + Ka,), dtype=torch.int64, device=dev)
+            na_g = torch.zeros((Wa + Ka + 1,), dtype=torch.int64, device=dev)
 
             def gsteps(k0, n):
                 for k in range(k0, k0 + n):
@@ -362,6 +392,40 @@ def run_ours(args):
                     eng.step_gather(k % R, k, b, k + 1, ll_of(b), o_mk[b], na_g[k:k + 1], stream)
                     eng.gather_wait(k + 1, cons)        # the consumer stream sees the whole gathered row ...
                     eng.gather_ack(k + 1, cons)         # ... and frees the buffer for sequence k + 1 + NB
+            # parity of the exchange (driver-visible on real peers): the first gathered row against every rank's own
+            # row of the same record from the plain step, collected with NCCL
+            eng.step_gather(0, 0, 0, 1, ll_of(0), o_mk[0], na_g[Wa + Ka:], stream)
+            eng.gather_wait(1, cons)
+            cons.synchronize()
+            got = eng.gather_buffer(0).clone()
+            eng.gather_ack(1, cons)
+            barrier()
+            reset()
+            eng.step(0, 0, o_yx[0], ll_of(0), o_mk[0], na_g[Wa + Ka:], stream)
+            stream.synchronize()
+            sendc = torch.zeros((npad, 2), dtype=torch.float64, device=dev)
+            sendc[:nP] = o_yx[0]
+            allc = torch.empty((world * npad, 2), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allc, sendc)
+            ok = True
+            for r in range(world):
+                ref_r = allc[r * npad: r * npad + int(cnts[r])]
+                ref_r = ref_r.to(torch.float32) if f4 else ref_r
+                ok = ok and bool(torch.equal(got[int(offs[r]): int(offs[r]) + int(cnts[r])], ref_r))
+            okt = torch.tensor([int(ok)], device=dev); dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            checks[tag] = "bit-identical on all %d ranks" % world if int(okt.item()) else "MISMATCH"
+            if not int(okt.item()):
+                log("[rank %d] gather check FAILED for %s" % (rank, tag))
+            del got, sendc, allc
+            # the gather protocol restarts from sequence 1 with fresh flags
+            eng.gather_destroy(); barrier()
+            reset(); torch.cuda.synchronize()
+            hnd = eng.gather_create(rank, world, int(offs[-1]), int(offs[rank]), f4=f4, nbuf=NB)
+            mine = torch.tensor(list(hnd), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine)
+            eng.gather_connect_ipc(bytes(allh.cpu().numpy().tobytes()))
+            eng.gather_set_mode(mode)
+            barrier()
             gsteps(0, Wa)
             barrier()
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -372,15 +436,35 @@ def run_ours(args):
             barrier()
             ms_g = max(t0.elapsed_time(t1), t0.elapsed_time(ec))     # until the last row has LANDED here too
             bad = eng.gather_timed_out()
-            ms_g, bs_g = reduce_max_sum(ms_g, int(na_g[Wa:].sum().item()))
+            ms_g, bs_g = reduce_max_sum(ms_g, int(na_g[Wa:Wa + Ka].sum().item()))
+            into = int((offs[-1] - cnts[rank]) * (8 if f4 else 16))
+            how = {0: "k_advect_warp stores every new (y,x) %s into the gathered array of all %d ranks itself "
+                      "(one NVLink peer store per thread per peer, ready/ack flags, no NCCL call)",
+                   1: "k_advect_warp writes its own block of (y,x) %s; one peer-to-peer copy per peer on the copy engines "
+                      "pushes it into the gathered arrays of all %d ranks (ready/ack flags, no NCCL call)",
+                   2: "k_advect_warp stages each tile of 32 (y,x) %s in shared memory and sends it to each of the %d ranks "
+                      "with one cp.async.bulk (peer order rotating per tile; ready/ack flags, no NCCL call)"}[mode]
             extra[tag] = {"value": bs_g / (ms_g * 1e-3), "unit": "buoy-steps/s", "steps": Ka,
-                          "bytes_into_each_rank_per_step": int((offs[-1] - cnts[rank]) * (8 if f4 else 16)),
-                          "timed_out": bool(bad),
-                          "what": "k_advect_warp stores every new (y,x) %s into the gathered array of all %d ranks "
-                                  "itself (NVLink peer stores, ready/ack flags, no NCCL call)" % ("f4" if f4 else "f8", world)}
+                          "ms_per_step": round(ms_g / Ka, 4),
+                          "bytes_into_each_rank_per_step": into,
+                          "ingress_gb_s": round(into / (ms_g / Ka * 1e-3) / 1e9, 1),
+                          "timed_out": bool(bad), "check": checks[tag],
+                          "what": how % ("f4" if f4 else "f8", world)}
             barrier()
             eng.gather_destroy()
             barrier()
+        # config 5 as BASELINE.json states it: every position on every GPU after every record
+        forms_done = [t for t in ("allgather", "allgather_fused", "allgather_bulk", "allgather_fused_f4",
+                                  "allgather_bulk_f4", "allgather_dma_f4") if t in extra and not extra[t].get("timed_out")]
+        if forms_done:
+            best = max(forms_done, key=lambda t: extra[t]["value"])
+            best8 = max([t for t in forms_done if not t.endswith("_f4")], key=lambda t: extra[t]["value"])
+            extra["with_allgather"] = {
+                "what": "BASELINE config 5 as stated: the per-record all-gather of positions inside the timed loop. "
+                        "`value` (above) is the same loop without the exchange.",
+                "best_form": best, "value": extra[best]["value"], "value_f8_positions": extra[best8]["value"],
+                "best_form_f8": best8, "unit": "buoy-steps/s",
+                "fraction_of_no_exchange_value": round(extra[best]["value"] / value, 4)}
 
     # -- e2e: host buffers in, host rows out, every step (pinned memory, 3 streams) ---------------
     Ke = args.e2e_steps if args.e2e_steps > 0 else max(4, min(K, 40 if nP > 2_000_000 else 200))
@@ -436,16 +520,17 @@ def run_ours(args):
             sec, bs = float(t.item()), float(s_.item())
         return sec, bs
 
-    e2e_s, e2e_bs = e2e_run(torch.float64)
-    e2e = {"value": e2e_bs / e2e_s, "unit": "buoy-steps/s", "h2d_bytes_per_step": int(3 * Nj * Ni * 4),
-           "d2h_bytes_per_step": int(D2H_PER_BUOY * nP), "steps": Ke, "ms_per_step": round(e2e_s / Ke * 1e3, 3),
-           "what": "per record: pinned host u/v/siconc -> st_upload_record -> st_step -> trajectory row "
-                   "(y,x,lat,lon f8 + mask) copied to pinned host memory and read"}
-    # the same through st_step_f4: rows in the dtype the reference's output files store (ncio.py:153-159)
+    # the end-to-end figure is what the command line does: rows leave the GPU in the dtype the reference's output
+    # files store (st_step_f4; ncio.py:153-159: every trajectory variable is f4), 17 B per buoy
     f4_s, f4_bs = e2e_run(torch.float32)
-    extra["e2e_file_dtype_rows"] = {"value": f4_bs / f4_s, "unit": "buoy-steps/s", "h2d_bytes_per_step": int(3 * Nj * Ni * 4),
-                                    "d2h_bytes_per_step": int(17 * nP), "steps": Ke, "ms_per_step": round(f4_s / Ke * 1e3, 3),
-                                    "what": "as e2e, rows as (y,x,lat,lon) f4 + mask = the f8 rows cast to the output file's dtype on the device"}
+    e2e = {"value": f4_bs / f4_s, "unit": "buoy-steps/s", "h2d_bytes_per_step": int(3 * Nj * Ni * 4),
+           "d2h_bytes_per_step": int(17 * nP), "steps": Ke, "ms_per_step": round(f4_s / Ke * 1e3, 3),
+           "what": "per record: pinned host u/v/siconc -> st_upload_record -> st_step_f4 -> trajectory row "
+                   "(y,x,lat,lon f4 + mask i1: the output file's dtypes) copied to pinned host memory and read"}
+    e2e_s, e2e_bs = e2e_run(torch.float64)
+    extra["e2e_f8_rows"] = {"value": e2e_bs / e2e_s, "unit": "buoy-steps/s", "h2d_bytes_per_step": int(3 * Nj * Ni * 4),
+                            "d2h_bytes_per_step": int(D2H_PER_BUOY * nP), "steps": Ke, "ms_per_step": round(e2e_s / Ke * 1e3, 3),
+                            "what": "as e2e with the rows as (y,x,lat,lon) f8 + mask, the reference's in-memory arrays"}
 
     # -- CPU baseline on this box's host cores (rank 0, N=1 only) ---------------------------------
     cpu = None
@@ -455,13 +540,16 @@ def run_ours(args):
 
     if rank == 0:
         out = {"metric": "buoy-steps/sec", "value": value, "unit": "buoy-steps/s", "n_gpus": world, "steps": K,
-               "warmup": W, "ms_per_step": round(ms_max / K, 5), "higher_is_better": True, "scaling": "weak",
+               "warmup": W, "ms_per_step": round(ms_max / K, 5), "higher_is_better": True,
+               "scaling": "strong" if strong else "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": wl["label"], "buoys_per_gpu": nP, "grid": [Nj, Ni],
                           "records_resident": R, "uv_strategy": 1, "rdt_s": 3600,
                           "l2": "inputs larger than L2: per step %.0f MB of buoy state + trajectory rows stream "
                                 "through, %d resident records (%.0f MB) are cycled; no flush"
                                 % (nP * B_ALG / 1e6, R, R * 3 * Nj * Ni * 4 / 1e6),
+                          "input_order": "as generated (cell-major)" if args.no_shuffle else
+                                         "random (shuffled); stored cell-major by the product (set_buoys sort)",
                           "parallelism": "buoys sharded over %d GPU(s), record replicated" % world},
                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
                "clocks": clocks, "seed_locate": {"buoys_per_s": SC_t.shape[0] / (seed_ms * 1e-3), "ms": round(seed_ms, 3)}}
@@ -663,6 +751,9 @@ def main():
     ap.add_argument("--no-latlon", action="store_true", help="diagnostic: skip the lat/lon row in the value loop")
     ap.add_argument("--multi", type=int, default=0, help="also time k_advect_multi with this many records per launch")
     ap.add_argument("--no-allgather", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: the workload's buoy count is the TOTAL, sharded over the ranks (config 4: --workload cfg4)")
+    ap.add_argument("--no-shuffle", action="store_true", help="diagnostic: feed the seeds in generator (cell-major) order, no sort")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2000, help="buoys in the Python cpu_baseline sample")
     ap.add_argument("--cpu-records", type=int, default=100)

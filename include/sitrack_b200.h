@@ -225,6 +225,14 @@ int  st_step_gather(st_ctx *ctx, int slot, int jrec, int buf, uint64_t seq, void
 int  st_gather_wait(st_ctx *ctx, uint64_t seq, void *stream);
 int  st_gather_ack(st_ctx *ctx, uint64_t seq, void *stream);
 int  st_gather_timed_out(st_ctx *ctx, int *timed_out);
+/* How st_step_gather moves this rank's rows to the peers (default 0; all three deliver the same bytes):
+ *   0  the step kernel stores every row into every peer's array itself (one 8- or 16-byte store per thread per peer);
+ *   1  the step kernel writes this rank's block only, then one peer-to-peer cudaMemcpyAsync per peer runs on the
+ *      copy engines (own streams) and the ready flags are released when they have landed;
+ *   2  the step kernel stages each tile of 32 rows in shared memory and sends it to each peer with one
+ *      cp.async.bulk (256 B as f4, 512 B as f8), peer order rotating with the tile.  Needs this rank's block to
+ *      start on an even row (falls back to 0 otherwise).                                                  */
+int  st_gather_set_mode(st_ctx *ctx, int mode);
 int  st_gather_destroy(st_ctx *ctx);
 
 /* ---- projections (util.py:394-472 via cartopy NorthPolarStereo) ------------------------ */

@@ -54,6 +54,9 @@ struct st_ctx {
         char* peer[ST_MAX_PEERS + 1] = {};    // every rank's block as mapped here (peer[rank] == base)
         bool ipc_opened[ST_MAX_PEERS + 1] = {};
         bool connected = false;
+        int mode = 0;                         // st_gather_set_mode: 0 per-thread peer stores, 1 copy engines, 2 bulk peer stores
+        cudaStream_t comm = nullptr, ps[ST_MAX_PEERS] = {};
+        cudaEvent_t ev_k = nullptr, ev_c[ST_MAX_PEERS] = {};
     } ga;
     // record slots
     std::vector<float*> d_rec, h_rec;
@@ -907,10 +910,31 @@ int st_step_gather(st_ctx* c, int slot, int jrec, int buf, uint64_t seq, void* o
     StepOut o{(pt*)(g.base + at), (pt*)out_latlon, out_mask, (unsigned long long*)n_alive};
     o.f4 = g.f4;
     o.npeer = 0;
+    o.bulk = 0;
+    if (c->variant == 4) { int rs = ensure_walk_scratch(c); if (rs) return rs; }
+    if (g.mode == 1 && g.world > 1) {
+        // copy engines: the kernel writes this rank's block only; one peer-to-peer copy per peer follows on its own
+        // stream, and the ready flags are released from a side stream once all of them have landed -- the caller's
+        // stream goes straight on to the next record
+        CU(c, launch_advect_step(c->grid, r, r + npt, r + 2 * npt, state_of(c), jrec, o, c->variant, (cudaStream_t)stream));
+        CU(c, cudaEventRecord(g.ev_k, (cudaStream_t)stream));
+        CU(c, cudaStreamWaitEvent(g.comm, g.ev_k, 0));
+        const size_t bytes = (size_t)c->nP * row;
+        for (int k = 1; k < g.world; ++k) {
+            const int pr = (g.rank + k) % g.world;
+            CU(c, cudaStreamWaitEvent(g.ps[k - 1], g.ev_k, 0));
+            CU(c, cudaMemcpyAsync(g.peer[pr] + at, g.base + at, bytes, cudaMemcpyDeviceToDevice, g.ps[k - 1]));
+            CU(c, cudaEventRecord(g.ev_c[k - 1], g.ps[k - 1]));
+            CU(c, cudaStreamWaitEvent(g.comm, g.ev_c[k - 1], 0));
+        }
+        return gather_signal_impl(c, 0, seq, g.comm);
+    }
     // each rank starts with its right-hand neighbour, so that at any moment the ranks' stores fan out
     // over different destinations instead of all converging on rank 0 first
     for (int k = 1; k < g.world; ++k) o.peer_yx[o.npeer++] = g.peer[(g.rank + k) % g.world] + at;
-    if (c->variant == 4) { int rs = ensure_walk_scratch(c); if (rs) return rs; }
+    // bulk peer stores need 16-byte aligned tiles in every rank's array: this rank's block must start on an even row
+    o.bulk = (g.mode == 2 && o.npeer > 0 && (c->variant == 0 || c->variant == 2 || c->variant == 3) &&
+              ((size_t)g.offset * row) % 16 == 0) ? 1 : 0;
     CU(c, launch_advect_step(c->grid, r, r + npt, r + 2 * npt, state_of(c), jrec, o, c->variant, (cudaStream_t)stream));
     return gather_signal_impl(c, 0, seq, stream);
 }
@@ -939,12 +963,34 @@ int st_gather_timed_out(st_ctx* c, int* timed_out)
     return ST_OK;
 }
 
+int st_gather_set_mode(st_ctx* c, int mode)
+{
+    if (!c || !c->ga.base) return fail(c, ST_ESTATE, "st_gather_set_mode: call st_gather_create first");
+    if (mode < 0 || mode > 2) return fail(c, ST_EINVAL, "st_gather_set_mode: 0 per-thread peer stores, 1 copy engines, 2 bulk peer stores");
+    st_ctx::Gather& g = c->ga;
+    CU(c, cudaSetDevice(c->device));
+    if (mode == 1 && !g.comm) {
+        CU(c, cudaStreamCreateWithFlags(&g.comm, cudaStreamNonBlocking));
+        CU(c, cudaEventCreateWithFlags(&g.ev_k, cudaEventDisableTiming));
+        for (int k = 0; k < g.world - 1; ++k) {
+            CU(c, cudaStreamCreateWithFlags(&g.ps[k], cudaStreamNonBlocking));
+            CU(c, cudaEventCreateWithFlags(&g.ev_c[k], cudaEventDisableTiming));
+        }
+    }
+    g.mode = mode;
+    return ST_OK;
+}
+
 int st_gather_destroy(st_ctx* c)
 {
     if (!c) return ST_OK;
     st_ctx::Gather& g = c->ga;
     if (g.base) {
         cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        if (g.comm) cudaStreamDestroy(g.comm);
+        if (g.ev_k) cudaEventDestroy(g.ev_k);
+        for (int k = 0; k < ST_MAX_PEERS; ++k) { if (g.ps[k]) cudaStreamDestroy(g.ps[k]); if (g.ev_c[k]) cudaEventDestroy(g.ev_c[k]); }
         for (int r = 0; r < g.world; ++r)
             if (g.ipc_opened[r] && g.peer[r]) cudaIpcCloseMemHandle(g.peer[r]);
         cudaFree(g.base);

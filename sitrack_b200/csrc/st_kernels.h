@@ -62,6 +62,9 @@ struct StepOut {
     // this rank's block of the gathered (nP_total,2) array.
     int npeer;
     void* peer_yx[ST_MAX_PEERS];
+    // bulk != 0 (k_advect_warp only): a warp stages the 32 rows of its tile in shared memory and sends them to each
+    // peer with ONE cp.async.bulk (256 B as f4, 512 B as f8) instead of 32 per-thread stores per peer
+    int bulk;
 };
 
 __device__ __forceinline__ void put_row_pt(void* base, long long p, pt v, int f4)

@@ -26,6 +26,8 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
     __shared__ pt qP[NW][QCAP], qPn[NW][QCAP];
     __shared__ int2 qC[NW][QCAP];
     __shared__ unsigned qI[NW][QCAP];
+    __shared__ __align__(128) double2 sRow[ROWS ? NW : 1][ROWS ? 32 : 1];    // tile staging of the bulk peer stores
+    bool bulk_pending = false;                                              // lane 0: a bulk group may still read sRow
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -133,6 +135,30 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
         if (valid) {
             if (ROWS == 0) {
                 if (o.yx) st_stream_pt(o.yx + p, outp);
+            } else if (o.bulk && (long long)tile * 32 + 32 <= s.nP) {      // warp-uniform: a full tile
+                // own block: plain row store; peers: the tile goes through shared memory and one bulk copy per peer
+                put_row_pt(o.yx, p, outp, o.f4);
+                if (lane == 0 && bulk_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                if (o.f4) reinterpret_cast<float2*>(sRow[wid])[lane] = make_float2(__double2float_rn(outp.y), __double2float_rn(outp.x));
+                else      sRow[wid][lane] = make_double2(outp.y, outp.x);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    const unsigned bytes = o.f4 ? 256u : 512u;
+                    const size_t at = (size_t)tile * bytes;
+                    const uint32_t src = smem_u32(sRow[wid]);
+                    // the peer order rotates with the tile, so that at any moment the warps of a GPU write to different peers
+                    int k = tile % o.npeer;
+#pragma unroll 1
+                    for (int q = 0; q < o.npeer; ++q) {
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(reinterpret_cast<char*>(o.peer_yx[k]) + at), "r"(src), "r"(bytes) : "memory");
+                        k = (k + 1 == o.npeer) ? 0 : k + 1;
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    bulk_pending = true;
+                }
             } else {
                 if (o.yx) put_row_yx(o, p, outp);
             }
@@ -159,6 +185,7 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
         }
         al = nal; P = nP_; c2 = nc2;
     }
+    if (ROWS && lane == 0 && bulk_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the peers' rows have left
     walk_pass(0, qn);                                             // flush (qn < 32)
     if (o.n_alive) {
         const int wsum = __reduce_add_sync(0xffffffffu, my_alive);

@@ -396,6 +396,10 @@ class TrackEngine:
         check(self.L.st_gather_timed_out(self.h, C.byref(v)), self.h)
         return bool(v.value)
 
+    def gather_set_mode(self, mode):
+        """0 per-thread peer stores (default), 1 copy engines, 2 bulk peer stores; see include/sitrack_b200.h."""
+        check(self.L.st_gather_set_mode(self.h, int(mode)), self.h)
+
     def gather_destroy(self):
         check(self.L.st_gather_destroy(self.h), self.h)
 

@@ -191,10 +191,12 @@ def test_file_dtype_rows_are_the_f4_cast_of_the_f8_rows(torch, gold_track):
             assert np.array_equal(r["posG"][1:], r8["posG"][1:].astype(np.float32))     # lat/lon: the cast of the f8 row
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["thread_stores", "copy_engines", "bulk_stores"])
 @pytest.mark.parametrize("f4", [False, True])
-def test_fused_position_allgather_two_ranks_one_device(torch, gold_track, f4):
+def test_fused_position_allgather_two_ranks_one_device(torch, gold_track, f4, mode):
     """st_step_gather: two contexts on cuda:0 play two ranks (st_gather_connect_ptrs).  Each owns a shard
-    of the golden cloud and its step kernel stores its rows into BOTH gathered arrays; after every record
+    of the golden cloud and its rows reach BOTH gathered arrays -- stored by the step kernel itself (per thread, or
+    a tile at a time through shared memory and cp.async.bulk) or pushed by the copy engines; after every record
     both arrays must equal the unsharded golden row -- the ready/ack flag protocol included (nbuf = 2)."""
     from sitrack_b200 import dist as sdist
     T, g = gold_track
@@ -211,6 +213,7 @@ def test_fused_position_allgather_two_ranks_one_device(torch, gold_track, f4):
         blocks = [eng.gather_block()[0] for eng in engs]
         for eng in engs:
             eng.gather_connect_ptrs(blocks)
+            eng.gather_set_mode(mode)
         streams = [torch.cuda.Stream(dev) for _ in range(2)]
         mks = [torch.empty((int(b[r + 1] - b[r]),), dtype=torch.int8, device=dev) for r in range(2)]
         for k in range(nrec):
