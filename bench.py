@@ -207,8 +207,8 @@ def run_ours(args):
     cell_t, near_t, keep_t = eng.seed_locate_dev(SG_t, SC_t, ic0_t)
     e1.record(); torch.cuda.synchronize()
     seed_ms = e0.elapsed_time(e1)
-    kp = keep_t.bool()
-    pos0_t, cell0_t = SC_t[kp].contiguous(), cell_t[kp].contiguous()
+    pos0_t, cell0_t = eng.seed_compact_dev(SC_t, cell_t, keep_t)     # SeedInit's shrink to the kept seeds, on the device
+    pos0_t, cell0_t = pos0_t.contiguous(), cell0_t.contiguous()
     nP = int(pos0_t.shape[0])
     if not args.no_shuffle:
         # the synthetic generator emits the cloud cell by cell; hand it to the product in RANDOM order, so that the

@@ -94,6 +94,11 @@ int  st_seed_locate_ex(st_ctx *ctx, int64_t nP, const double *SG, const double *
 int  st_seed_locate_dev(st_ctx *ctx, int64_t nP, const double *SG_dev, const double *SC_dev,
                         const float *ic0_dev, int32_t *cell_dev, int32_t *nearest_dev, int8_t *keep_dev,
                         void *stream);
+/* SeedInit's shrink to the kept buoys (tracking.py:166-178) on the device: pos (nP,2) f8 and cell (nP,2) i4 compacted
+ * by keep (nP) i1 into out_pos / out_cell (capacity nP), order kept; *n_out = buoys kept.  Device pointers; synchronises
+ * `stream` (the count comes back to the host).                                                             */
+int  st_seed_compact_dev(st_ctx *ctx, int64_t nP, const double *pos_dev, const int32_t *cell_dev, const int8_t *keep_dev,
+                         double *out_pos_dev, int32_t *out_cell_dev, int64_t *n_out, void *stream);
 /* NearestPoint alone (locate.py:222-276; no ji_prv box).  Host in/out.
  * use_brute != 0 runs the reference's own whole-grid scan on the device instead of
  * the hash search (cross-check).                                                        */

@@ -51,6 +51,8 @@ def __argument_parsing__():
     parser.add_argument('--sort', action="store_true",
                         help='store and write the buoys in cell-major order (much faster gathers on large clouds); the '
                              'output files then list the buoys, with their IDs, in that order instead of seed order')
+    parser.add_argument('--no-chunk', action="store_true",
+                        help='small clouds: one kernel launch per record (streaming) instead of one per chunk of records')
     parser.add_argument('--rows', default='f4', choices=['f4', 'f8'],
                         help='dtype of the trajectory rows copied off the GPU: f4 = the dtype the output files store (default), f8 = full in-memory arrays as upstream')
     args = parser.parse_args()
@@ -253,8 +255,18 @@ def main():
     if args.scheme != 'euler' or args.interp != 'pick' or args.hops != 1:
         physics = dict(scheme={'euler': 1, 'rk2': 2, 'rk4': 4}[args.scheme], interp=int(args.interp == 'linear'), max_hops=args.hops)
         print(' *** NOTE: optional physics beyond upstream sitrack is ON:', physics)
-    res = eng.track(record, Nt, kstrt=kstrt, rec_first=cut(z1st), sink=sink,
-                    row_dtype='f8' if physics else args.rows, physics=physics)
+    # small clouds are launch-bound: a whole chunk of records per launch (k_advect_multi, 4 us per record instead of
+    # 11 us) and the rows of the chunk come back together; large clouds stream row by row
+    small = world == 1 and physics is None and nP <= 262144 and nP * (Nt + 1) * 17 < 2e9 and not args.no_chunk
+    if small:
+        nchunk = max(2, min(Nt, 48, int(256e6 // (3 * Nj * Ni * 4))))      # <= 256 MB of pinned records per slot
+        res = eng.track(record, Nt, kstrt=kstrt, pos0=xPosC0, posG0=xPosG0, rec_first=z1st, chunk=nchunk,
+                        row_dtype=args.rows)
+        for k in range(Nt):
+            keep_row(k, res['posC'][k + 1], res['posG'][k + 1], res['mask'][k + 1])
+    else:
+        res = eng.track(record, Nt, kstrt=kstrt, rec_first=cut(z1st), sink=sink,
+                        row_dtype='f8' if physics else args.rows, physics=physics)
     eng.close()
     ds.close()
     n_alive = res['n_alive']

@@ -39,6 +39,7 @@ SIGNATURES = {
     "st_selftest_cert": (c_int, [vp, c_i64, vp, vp, vp, vp]),
     "st_set_locate_grid": (c_int, [vp, vp, vp, vp]),
     "st_seed_locate": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp]),
+    "st_seed_compact_dev": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, C.POINTER(c_i64), vp]),
     "st_seed_locate_ex": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "st_seed_locate_dev": (c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp]),
     "st_nearest_point": (c_int, [vp, c_i64, vp, c_dbl, c_int, c_int, vp, vp]),

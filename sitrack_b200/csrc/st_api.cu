@@ -396,6 +396,23 @@ int st_seed_locate_dev(st_ctx* c, int64_t nP, const double* SG, const double* SC
     return ST_OK;
 }
 
+int st_seed_compact_dev(st_ctx* c, int64_t nP, const double* pos, const int32_t* cell, const int8_t* keep,
+                        double* out_pos, int32_t* out_cell, int64_t* n_out, void* stream)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (nP < 0 || !pos || !cell || !keep || !out_pos || !out_cell || !n_out) return fail(c, ST_EINVAL, "st_seed_compact_dev: NULL argument");
+    CU(c, cudaSetDevice(c->device));
+    long long* d_n = nullptr;
+    CU(c, cudaMalloc(&d_n, sizeof(long long)));
+    cudaError_t e = seed_compact(nP, (const pt*)pos, (const int2*)cell, keep, (pt*)out_pos, (int2*)out_cell, d_n, (cudaStream_t)stream);
+    long long n = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&n, d_n, sizeof(n), cudaMemcpyDeviceToHost);
+    cudaFree(d_n);
+    if (e != cudaSuccess) return cuda_fail(c, e, "st_seed_compact_dev");
+    *n_out = n;
+    return ST_OK;
+}
+
 int st_seed_locate_ex(st_ctx* c, int64_t nP, const double* SG, const double* SC, const float* ic0,
                       int32_t* cell, int32_t* nearest, int8_t* keep, int8_t* flag, int32_t* first, int32_t* second)
 {

@@ -136,6 +136,8 @@ struct SeedOut {
 
 cudaError_t locate_build(int Nj, int Ni, const double* d_lat, const double* d_lon, const double* d_res,
                          LocateGrid* out, int** owned_start, int** owned_pts, cudaStream_t st);
+cudaError_t seed_compact(long long nP, const pt* pos, const int2* cell, const int8_t* keep, pt* out_pos, int2* out_cell,
+                         long long* d_nout, cudaStream_t st);
 cudaError_t launch_seed_locate(const LocateGrid& lg, const AdvectGrid& g, const float* ic0,
                                long long nP, const pt* SG, const pt* SC, const SeedOut& o,
                                int do_survive, int do_cell, cudaStream_t st);

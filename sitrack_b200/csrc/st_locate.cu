@@ -18,6 +18,8 @@
 //   Ties on equal distance resolve to the lower flat index like numpy's argmin.
 #include "st_kernels.h"
 #include <math.h>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 
 namespace st {
 
@@ -32,38 +34,55 @@ __device__ __forceinline__ void plane_of(double lat, double lon, double& px, dou
 }
 
 // ---- build ---------------------------------------------------------------------------
-__global__ void k_plane_bounds(const double* __restrict__ lat, const double* __restrict__ lon,
-                               const double* __restrict__ res, int n, double* __restrict__ px,
-                               double* __restrict__ py, double* __restrict__ red /*[6]*/)
+// plane coordinates of every T-point and, per block, the partial extrema {xmin, xmax, ymin, ymax, q2max, resmax}
+// (part[6 * blockIdx.x ...]); k_bounds_finish folds the partials.  Grid-stride, one block per SM or more.
+__device__ __forceinline__ void reduce6(double v[6])
 {
-    // single block: xmin, xmax, ymin, ymax, q2max, resmax
-    __shared__ double sh[6][32];
-    double v[6] = {1e300, -1e300, 1e300, -1e300, 0.0, 0.0};
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        double x, y; plane_of(lat[k], lon[k], x, y);
-        px[k] = x; py[k] = y;
-        v[0] = fmin(v[0], x); v[1] = fmax(v[1], x); v[2] = fmin(v[2], y); v[3] = fmax(v[3], y);
-        v[4] = fmax(v[4], x * x + y * y);
-        if (res) v[5] = fmax(v[5], res[k]);
-    }
     for (int o = 16; o; o >>= 1) {
         v[0] = fmin(v[0], __shfl_xor_sync(~0u, v[0], o)); v[1] = fmax(v[1], __shfl_xor_sync(~0u, v[1], o));
         v[2] = fmin(v[2], __shfl_xor_sync(~0u, v[2], o)); v[3] = fmax(v[3], __shfl_xor_sync(~0u, v[3], o));
         v[4] = fmax(v[4], __shfl_xor_sync(~0u, v[4], o)); v[5] = fmax(v[5], __shfl_xor_sync(~0u, v[5], o));
     }
+}
+__device__ __forceinline__ void block_reduce6(double v[6], double* __restrict__ out)
+{
+    __shared__ double sh[6][32];
+    reduce6(v);
     const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
     if (ln == 0) for (int q = 0; q < 6; ++q) sh[q][w] = v[q];
     __syncthreads();
     if (w == 0) {
         const int nw = blockDim.x >> 5;
         for (int q = 0; q < 6; ++q) v[q] = (ln < nw) ? sh[q][ln] : ((q == 0 || q == 2) ? 1e300 : (q < 4 ? -1e300 : 0.0));
-        for (int o = 16; o; o >>= 1) {
-            v[0] = fmin(v[0], __shfl_xor_sync(~0u, v[0], o)); v[1] = fmax(v[1], __shfl_xor_sync(~0u, v[1], o));
-            v[2] = fmin(v[2], __shfl_xor_sync(~0u, v[2], o)); v[3] = fmax(v[3], __shfl_xor_sync(~0u, v[3], o));
-            v[4] = fmax(v[4], __shfl_xor_sync(~0u, v[4], o)); v[5] = fmax(v[5], __shfl_xor_sync(~0u, v[5], o));
-        }
-        if (ln == 0) for (int q = 0; q < 6; ++q) red[q] = v[q];
+        reduce6(v);
+        if (ln == 0) for (int q = 0; q < 6; ++q) out[q] = v[q];
     }
+}
+__global__ void __launch_bounds__(256)
+k_plane_bounds(const double* __restrict__ lat, const double* __restrict__ lon,
+               const double* __restrict__ res, int n, double* __restrict__ px,
+               double* __restrict__ py, double* __restrict__ part /*[6 * gridDim.x]*/)
+{
+    double v[6] = {1e300, -1e300, 1e300, -1e300, 0.0, 0.0};
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        double x, y; plane_of(lat[k], lon[k], x, y);
+        px[k] = x; py[k] = y;
+        v[0] = fmin(v[0], x); v[1] = fmax(v[1], x); v[2] = fmin(v[2], y); v[3] = fmax(v[3], y);
+        v[4] = fmax(v[4], x * x + y * y);
+        if (res) v[5] = fmax(v[5], res[k]);
+    }
+    block_reduce6(v, part + 6 * blockIdx.x);
+}
+__global__ void __launch_bounds__(256)
+k_bounds_finish(const double* __restrict__ part, int nblk, double* __restrict__ red /*[6]*/)
+{
+    double v[6] = {1e300, -1e300, 1e300, -1e300, 0.0, 0.0};
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+        const double* q = part + 6 * b;
+        v[0] = fmin(v[0], q[0]); v[1] = fmax(v[1], q[1]); v[2] = fmin(v[2], q[2]); v[3] = fmax(v[3], q[3]);
+        v[4] = fmax(v[4], q[4]); v[5] = fmax(v[5], q[5]);
+    }
+    block_reduce6(v, red);
 }
 
 __device__ __forceinline__ int bin_of(double x, double y, double x0, double y0, double inv_bin, int nbx, int nby)
@@ -78,23 +97,6 @@ __global__ void k_bin_count(const double* __restrict__ px, const double* __restr
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) atomicAdd(cnt + bin_of(px[k], py[k], x0, y0, inv_bin, nbx, nby), 1);
-}
-
-// single-block exclusive scan (setup-time only): start[0..nb] from cnt[0..nb-1]
-__global__ void k_bin_scan(const int* __restrict__ cnt, int nb, int* __restrict__ start)
-{
-    __shared__ int part[1024];
-    const int T = blockDim.x, t = threadIdx.x;
-    const int chunk = (nb + T - 1) / T;
-    const int lo = min(t * chunk, nb), hi = min(lo + chunk, nb);
-    int s = 0;
-    for (int k = lo; k < hi; ++k) s += cnt[k];
-    part[t] = s;
-    __syncthreads();
-    if (t == 0) { int acc = 0; for (int q = 0; q < T; ++q) { const int c = part[q]; part[q] = acc; acc += c; } start[nb] = acc; }
-    __syncthreads();
-    int acc = part[t];
-    for (int k = lo; k < hi; ++k) { start[k] = acc; acc += cnt[k]; }
 }
 
 __global__ void k_bin_fill(const double* __restrict__ px, const double* __restrict__ py, int n,
@@ -114,11 +116,15 @@ cudaError_t locate_build(int Nj, int Ni, const double* d_lat, const double* d_lo
     const int n = Nj * Ni;
     double *px = nullptr, *py = nullptr, *red = nullptr;
     int *cnt = nullptr, *start = nullptr, *pts = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const int nblk = 592;                                     // 4 blocks per SM of a B200
     cudaError_t e;
 #define CK(x) do { e = (x); if (e != cudaSuccess) goto fail; } while (0)
     CK(cudaMalloc(&px, sizeof(double) * n)); CK(cudaMalloc(&py, sizeof(double) * n));
-    CK(cudaMalloc(&red, sizeof(double) * 6));
-    k_plane_bounds<<<1, 1024, 0, st>>>(d_lat, d_lon, d_res, n, px, py, red);
+    CK(cudaMalloc(&red, sizeof(double) * 6 * (nblk + 1)));
+    k_plane_bounds<<<nblk, 256, 0, st>>>(d_lat, d_lon, d_res, n, px, py, red + 6);
+    k_bounds_finish<<<1, 256, 0, st>>>(red + 6, nblk, red);
     double h[6];
     CK(cudaMemcpyAsync(h, red, sizeof(h), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -127,12 +133,15 @@ cudaError_t locate_build(int Nj, int Ni, const double* d_lat, const double* d_lo
         double bin = sqrt(w * ht * 2.0 / n);                  // ~2 T-points per bin
         int nbx = (int)(w / bin) + 1, nby = (int)(ht / bin) + 1;
         const int nb = nbx * nby;
-        CK(cudaMalloc(&cnt, sizeof(int) * nb)); CK(cudaMalloc(&start, sizeof(int) * (nb + 1)));
+        CK(cudaMalloc(&cnt, sizeof(int) * (nb + 1))); CK(cudaMalloc(&start, sizeof(int) * (nb + 1)));
         CK(cudaMalloc(&pts, sizeof(int) * n));
-        CK(cudaMemsetAsync(cnt, 0, sizeof(int) * nb, st));
+        CK(cudaMemsetAsync(cnt, 0, sizeof(int) * (nb + 1), st));
         const int B = 256, G = (n + B - 1) / B;
         k_bin_count<<<G, B, 0, st>>>(px, py, n, h[0], h[2], 1.0 / bin, nbx, nby, cnt);
-        k_bin_scan<<<1, 1024, 0, st>>>(cnt, nb, start);
+        // start[0..nb] = exclusive prefix sum of cnt[0..nb] (cnt[nb] = 0): CUB's device-wide scan (setup, once per grid)
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, start, nb + 1, st));
+        CK(cudaMalloc(&tmp, tmp_bytes));
+        CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, start, nb + 1, st));
         CK(cudaMemsetAsync(cnt, 0, sizeof(int) * nb, st));
         k_bin_fill<<<G, B, 0, st>>>(px, py, n, h[0], h[2], 1.0 / bin, nbx, nby, start, cnt, pts);
         CK(cudaGetLastError());
@@ -142,10 +151,10 @@ cudaError_t locate_build(int Nj, int Ni, const double* d_lat, const double* d_lo
         out->q2max = h[4]; out->res_max = h[5]; out->bin_start = start; out->bin_pts = pts;
         *owned_start = start; *owned_pts = pts;
     }
-    cudaFree(px); cudaFree(py); cudaFree(red); cudaFree(cnt);
+    cudaFree(px); cudaFree(py); cudaFree(red); cudaFree(cnt); cudaFree(tmp);
     return cudaSuccess;
 fail:
-    cudaFree(px); cudaFree(py); cudaFree(red); cudaFree(cnt); cudaFree(start); cudaFree(pts);
+    cudaFree(px); cudaFree(py); cudaFree(red); cudaFree(cnt); cudaFree(start); cudaFree(pts); cudaFree(tmp);
     return e;
 #undef CK
 }
@@ -318,6 +327,25 @@ cudaError_t launch_seed_locate(const LocateGrid& lg, const AdvectGrid& g, const 
 {
     // SeedInit's call: rd_found_km=2.5 (overridden by 0.5*resKM), max_itr=10 (tracking.py:134)
     return launch_seed_locate_opt(lg, g, ic0, nP, SG, SC, o, g_default_opt.rd_found_km, 10, do_survive, do_cell, st);
+}
+
+// SeedInit's shrink to the kept buoys (tracking.py:166-178) on the device: pos and cell compacted by `keep`, order kept
+cudaError_t seed_compact(long long nP, const pt* pos, const int2* cell, const int8_t* keep, pt* out_pos, int2* out_cell,
+                         long long* d_nout, cudaStream_t st)
+{
+    if (nP <= 0) return cudaMemsetAsync(d_nout, 0, sizeof(long long), st);
+    void* tmp = nullptr;
+    size_t b1 = 0, b2 = 0;
+    const double2* p2 = reinterpret_cast<const double2*>(pos);
+    double2* o2 = reinterpret_cast<double2*>(out_pos);
+    cudaError_t e = cub::DeviceSelect::Flagged(nullptr, b1, p2, keep, o2, d_nout, nP, st);
+    if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(nullptr, b2, cell, keep, out_cell, d_nout, nP, st);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, b1 > b2 ? b1 : b2);
+    if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(tmp, b1, p2, keep, o2, d_nout, nP, st);
+    if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(tmp, b2, cell, keep, out_cell, d_nout, nP, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    return e;
 }
 
 cudaError_t launch_nearest_brute(const LocateGrid& lg, long long nP, const pt* SG, int2* nearest,

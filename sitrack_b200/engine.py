@@ -202,6 +202,17 @@ class TrackEngine:
                                         _dptr(near), _dptr(keep), _sptr(stream)), self.h)
         return cell, near, keep
 
+    def seed_compact_dev(self, pos_t, cell_t, keep_t, stream=None):
+        """(pos, cell) of the kept seeds, order kept (SeedInit's shrink, tracking.py:166-178), on the device."""
+        torch = _torch()
+        stream = stream or torch.cuda.current_stream(pos_t.device)
+        nP = pos_t.shape[0]
+        out_pos, out_cell = torch.empty_like(pos_t), torch.empty_like(cell_t)
+        n = C.c_int64(0)
+        check(self.L.st_seed_compact_dev(self.h, nP, _dptr(pos_t), _dptr(cell_t), _dptr(keep_t), _dptr(out_pos),
+                                         _dptr(out_cell), C.byref(n), _sptr(stream)), self.h)
+        return out_pos[:n.value], out_cell[:n.value]
+
     def nearest_point(self, latlon, rd_found_km=2.5, max_itr=10, brute=False):
         ll = as_c(latlon, np.float64).reshape(-1, 2)
         ji = np.zeros((ll.shape[0], 2), np.int32)
@@ -520,18 +531,7 @@ class TrackEngine:
         if perm is not None:                                # engine order -> the caller's order
             inv = np.empty_like(perm); inv[perm] = np.arange(perm.size)
             posC, posG, mask = posC[:, inv], posG[:, inv], mask[:, inv]
-        if pos0 is not None:
-            if rec_first is None:
-                posC[0] = pos0; mask[0] = 1
-                if posG0 is not None:
-                    posG[0] = posG0
-            else:                                           # si3_part_tracker.py:335-340
-                for b in range(nP):
-                    k0 = int(rec_first[b]) - kstrt
-                    if k0 == 0:
-                        posC[0, b] = pos0[b]; mask[0, b] = 1
-                        if posG0 is not None:
-                            posG[0, b] = posG0[b]
+        _finish_rows(posC, posG, mask, pos0, posG0, rec_first, kstrt)
         return dict(posC=posC, posG=posG, mask=mask, n_alive=n_alive)
 
 
