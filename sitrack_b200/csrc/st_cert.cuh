@@ -109,7 +109,7 @@ __device__ __forceinline__ CertLane cert_eval(const float4 f0, const float4 f1, 
 // `alive` is bit 31 of the cell's jT word.
 constexpr int ST_CERT_BLOCK = 256;
 #ifndef ST_CERT_MINBLK
-#define ST_CERT_MINBLK 6                                          // 1536 resident threads per SM at <= 42 registers
+#define ST_CERT_MINBLK 8                                          // full occupancy: 2048 resident threads per SM at 32 registers (12 B of spill; 6 blocks x 40 registers measured slower)
 #endif
 #ifndef ST_WALK_TILES
 #define ST_WALK_TILES 24
