@@ -225,6 +225,26 @@ def main():
                         out_jiT=zjiT, out_VRTCS=zJIvrt, out_iKeep=iKeep, out_nearest=near)
     print("seedinit_small: %d seeds -> %d kept" % (SG.shape[0], nP))
 
+    # NearestPoint with the `ji_prv` local box (locate.py:241-244,255-256; FCC forwards it at :180): the box around a
+    # previous guess is searched first, the whole domain only when that fails; note that the first radius is
+    # 0.5*resolkm[jy,jx] with (jy,jx) the BOX-LOCAL indices of the box's argmin (upstream quirk, kept)
+    rng = np.random.default_rng(21)
+    nb_pt, nb_prv, nb_r, nb_out = [], [], [], []
+    for k in range(SG.shape[0]):
+        for rep in range(2):
+            far = rng.random() < 0.3
+            j0 = int(near[k][0]) if near[k][0] >= 0 else int(rng.integers(0, small["Nj"]))
+            i0 = int(near[k][1]) if near[k][1] >= 0 else int(rng.integers(0, small["Ni"]))
+            off = rng.integers(-25, 26, 2) if far else rng.integers(-4, 5, 2)
+            jp = int(np.clip(j0 + off[0], 0, small["Nj"] - 1)); ip = int(np.clip(i0 + off[1], 0, small["Ni"] - 1))
+            rbox = int(rng.choice([3, 10]))
+            out = quiet(sit.NearestPoint, (SG[k, 0], SG[k, 1]), small["latT"], small["lonT"], rd_found_km=2.5,
+                        resolkm=small["ResKM"], ji_prv=(jp, ip), np_box_r=rbox, max_itr=10)
+            nb_pt.append(SG[k]); nb_prv.append((jp, ip)); nb_r.append(rbox); nb_out.append(out)
+    np.savez_compressed(os.path.join(GOLD, "nearest_box.npz"), pt=np.array(nb_pt), ji_prv=np.array(nb_prv),
+                        np_box_r=np.array(nb_r), out=np.array(nb_out))
+    print("nearest_box: %d cases, %d not found" % (len(nb_out), int((np.array(nb_out)[:, 0] < 0).sum())))
+
     # ---- tracking on the 'tiny' grid, 48 records ---------------------------------------
     ids_t, SG_t, SC_t = synth.hss_seeds(tiny, IC[0], khss=2)
     xic = np.zeros(tiny["tmask"].shape); xic[:, :] = IC[0]

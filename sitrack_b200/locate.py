@@ -148,14 +148,41 @@ def NearestPointBatch(latlon, pLat, pLon, rd_found_km=10., resolkm=None, max_itr
         return eng.nearest_point(latlon, rd_found_km=rd_found_km, max_itr=max_itr, brute=brute)
 
 
+def _nearest_point_box(pntGcoor, pLat, pLon, rd_found_km, resolkm, ji_prv, np_box_r, max_itr):
+    """NearestPoint with a previous guess (locate.py:241-244,255-256): pass 1 looks at the box of half-width
+    `np_box_r` around `ji_prv` only -- a few hundred points, evaluated here with numpy, the reference's own
+    arithmetic -- and passes 2.. fall back on the whole domain (device search).  Upstream quirks kept: the first
+    radius is 0.5*resolkm[jy,jx] with (jy,jx) the BOX-LOCAL indices of the box's argmin (:262), it is not grown
+    after pass 1 (:268 needs igo > 1), and a hit on pass `max_itr` is thrown away (:274)."""
+    (Ny, Nx) = pLat.shape
+    l2Dresol = np.shape(resolkm) == (Ny, Nx)
+    (latP, lonP) = pntGcoor
+    (j_prv, i_prv) = ji_prv
+    j1, j2 = max(j_prv - np_box_r, 0), min(j_prv + np_box_r + 1, Ny)
+    i1, i2 = max(i_prv - np_box_r, 0), min(i_prv + np_box_r + 1, Nx)
+    xd = _haversine_host(latP, lonP, np.asarray(pLat)[j1:j2, i1:i2], np.asarray(pLon)[j1:j2, i1:i2])
+    jy, jx = find_ji_of_min(xd)
+    rfnd = 0.5 * np.asarray(resolkm)[jy, jx] if l2Dresol else rd_found_km
+    if max_itr > 1 and xd[jy, jx] < rfnd:
+        return (int(jy + j1), int(jx + i1))
+    if max_itr <= 2:                                           # pass 2 would be the last one: its hit is discarded
+        print('    WARNING [NearestPoint()]: did not find a nearest point for target point ', latP, lonP, ' !')
+        return (-1, -1)
+    # whole domain, radii rfnd * 1.2^(igo-2) for igo = 2 .. max_itr-1: the no-box ladder started at rfnd
+    ji, d = NearestPointBatch([pntGcoor], pLat, pLon, float(rfnd), None, max_itr)
+    jy, jx = int(ji[0, 0]), int(ji[0, 1])
+    if jy < 0:
+        print('    WARNING [NearestPoint()]: did not find a nearest point for target point ', latP, lonP, ' !')
+    return (jy, jx)
+
+
 def NearestPoint(pntGcoor, pLat, pLon, rd_found_km=10., resolkm=[], ji_prv=(), np_box_r=10, max_itr=5):
     """locate.py:222-276 -> (jy,jx) of the nearest grid point, or (-1,-1)."""
     if np.shape(pLon) != np.shape(pLat):
         print('ERROR [NearestPoint]: `pLat` & `pLon` do not have the same shape!')
         raise SystemExit(0)
     if len(ji_prv) == 2:
-        raise NotImplementedError("NearestPoint: the `ji_prv` local-box variant is not used by the tracker "
-                                  "and is not provided by sitrack_b200")
+        return _nearest_point_box(pntGcoor, pLat, pLon, rd_found_km, resolkm, ji_prv, np_box_r, max_itr)
     res = resolkm if np.shape(resolkm) == np.shape(pLat) else None
     ji, d = NearestPointBatch([pntGcoor], pLat, pLon, rd_found_km, res, max_itr)
     jy, jx = int(ji[0, 0]), int(ji[0, 1])

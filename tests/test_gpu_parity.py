@@ -5,6 +5,8 @@ Bars: cell indices, alive flags, masks, alive counts and f8 positions bit-exact 
 operation is an un-fused IEEE double op in the reference's order); lat/lon within
 1e-9 degrees of the PROJ-style iterative inverse (PROJ itself iterates to 1e-10 rad).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -766,3 +768,21 @@ def test_seed_locate_near_ties_are_rechecked_on_the_host(torch):
         want = (jy, jx) if d[jy, jx] < rf else (-1, -1)
         assert (int(near[p, 0]), int(near[p, 1])) == want, (p, near[p], near0[p], want)
     assert n_tie > 100
+
+
+def test_nearest_point_with_previous_guess_golden(sit, gold_seed):
+    """NearestPoint(ji_prv=..., np_box_r=...) (locate.py:241-244,255-256; FCC forwards it) against the reference's
+    answers on 648 cases (tests/golden/nearest_box.npz, generated by oracle/make_golden.py from the unmodified
+    reference): guesses near and far from the true nearest point, boxes of half-width 3 and 10, seeds that end as
+    (-1,-1)."""
+    import contextlib, io
+    S, g = gold_seed
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "nearest_box.npz"))
+    sel = np.arange(0, G["pt"].shape[0], 3)                        # every third case: each one is its own launch
+    n_box = 0
+    for k in sel:
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = sit.NearestPoint(tuple(G["pt"][k]), g["latT"], g["lonT"], rd_found_km=2.5, resolkm=g["ResKM"],
+                                   ji_prv=tuple(int(v) for v in G["ji_prv"][k]), np_box_r=int(G["np_box_r"][k]), max_itr=10)
+        assert tuple(got) == tuple(int(v) for v in G["out"][k]), (k, got, G["out"][k])
+    assert (G["out"][sel][:, 0] < 0).sum() > 5 and (G["out"][sel][:, 0] >= 0).sum() > 100
