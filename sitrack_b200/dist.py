@@ -3,9 +3,12 @@ si3_part_tracker.py:378-488), one process per GPU, the static grid and the curre
 replicated.  The only collectives are the optional per-output-record all-gather of trajectory
 rows and the all-reduce of the alive count.  Two forms of the all-gather:
   * RowGatherer: torch.distributed all_gather_into_tensor (NCCL on GPUs, gloo in the CPU tests);
-  * PeerGather: fused into the step kernel -- every rank's k_advect_persist stores its new positions
-    straight into the gathered array of all ranks over NVLink peer memory (st_step_gather); here
-    torch.distributed only carries the 64-byte CUDA IPC handles once, at set-up.
+  * PeerGather: fused into the step kernel -- every rank's k_advect_warp stores its new positions
+    straight into the gathered array of all ranks over NVLink peer memory (st_step_gather; `mode` picks per-thread
+    peer stores, copy engines or cp.async.bulk tile stores); here torch.distributed only carries the 64-byte CUDA
+    IPC handles once, at set-up.  Shards are tile-aligned (TILE rows): a rank's block of the gathered array must
+    start on a multiple of 32 rows for its warps' peer stores to cover whole sectors at the receiver (a quarter of
+    the NVLink throughput is lost otherwise).
 """
 import numpy as np
 
@@ -74,9 +77,13 @@ class PeerGather:
             pg.release(consumer_stream)                    # the buffer may be overwritten nbuf records later
     """
 
-    def __init__(self, engine, n_global, offset, f4=False, nbuf=2, group=None):
+    def __init__(self, engine, n_global, offset, f4=False, nbuf=2, group=None, mode=0):
         import torch.distributed as dist
         self.eng, self.nbuf, self.seq = engine, int(nbuf), 0
+        if offset % 32:
+            import warnings
+            warnings.warn("PeerGather: this rank's block starts at row %d, not a multiple of 32: its peer stores will "
+                          "straddle sectors (use dist.shard_bounds)" % offset)
         if dist.is_available() and dist.is_initialized():
             rank, world = dist.get_rank(group), dist.get_world_size(group)
         else:
@@ -87,6 +94,8 @@ class PeerGather:
             dist.all_gather_object(handles, handle, group=group)
             engine.gather_connect_ipc(handles)
             dist.barrier(group)                            # every rank has mapped every block
+        if mode:
+            engine.gather_set_mode(mode)
 
     def step(self, slot, jrec, out_latlon=None, out_mask=None, n_alive=None, stream=None):
         self.seq += 1

@@ -1,7 +1,10 @@
 """GPU, world_size 2 over real peer memory (needs two devices; skipped on a one-GPU box): every rank's step
 kernel stores its shard's new positions into BOTH ranks' gathered arrays through CUDA-IPC-mapped HBM
-(st_step_gather, sitrack_b200.dist.PeerGather).  After each record each rank's gathered array must equal
-the row of the unsharded run by the C oracle, bit for bit, and match the NCCL all-gather of the same rows."""
+(st_step_gather, sitrack_b200.dist.PeerGather; per-thread peer stores, copy engines or cp.async.bulk tile stores).
+After each record each rank's gathered array must equal the row of the unsharded run by the C oracle, bit for bit,
+and the NCCL all-gather (sitrack_b200.dist.RowGatherer) of every rank's own block of it must reproduce it.  (On a
+one-GPU box the same protocol runs with two contexts on one device in tests/test_gpu_parity.py, and every multi-GPU
+`bench.py` run checks the exchange against NCCL on all ranks.)"""
 import os
 import socket
 import sys
@@ -18,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, f4, q):
+def _worker(rank, world, port, f4, mode, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -39,7 +42,7 @@ def _worker(rank, world, port, f4, q):
         pos0 = np.concatenate([z["pos0"] + rng.uniform(-0.5, 0.5, z["pos0"].shape) for _ in range(rep)])
         cell0 = np.concatenate([z["jiT0"]] * rep).astype(np.int32)
         n = pos0.shape[0]
-        b = shard_bounds(n, world, tile=64)
+        b = shard_bounds(n, world)
         lo, hi = int(b[rank]), int(b[rank + 1])
         nrec = 16
         U, V, IC = 3 * z["U"][:nrec], 3 * z["V"][:nrec], z["IC"][:nrec]
@@ -47,7 +50,9 @@ def _worker(rank, world, port, f4, q):
         with engine_for(g, device=rank) as eng:
             eng.set_buoys(pos0[lo:hi], cell0[lo:hi])
             eng.record_slots(2)
-            pg = PeerGather(eng, n, lo, f4=f4, nbuf=2)
+            pg = PeerGather(eng, n, lo, f4=f4, nbuf=2, mode=mode)
+            rg = RowGatherer(n, world, rank, width=2, dtype=torch.float32 if f4 else torch.float64, device=dev)
+            assert np.array_equal(rg.b, b) and TILE_OK(b, rg.b)
             s_cmp, s_con = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             mk = torch.empty((hi - lo,), dtype=torch.int8, device=dev)
             na = torch.zeros((nrec,), dtype=torch.int64, device=dev)
@@ -62,6 +67,12 @@ def _worker(rank, world, port, f4, q):
                 with torch.cuda.stream(s_con):
                     keep.append(row.clone())                # the consumer: a copy on the consumer stream
                 pg.release(s_con)
+                if k == nrec - 1:                           # the same row through NCCL, from every rank's own block
+                    s_con.synchronize()
+                    rg.gather(keep[-1][lo:hi])
+                    torch.cuda.synchronize()
+                    if not torch.equal(rg.result(), keep[-1]):
+                        status = "NCCL gather differs on rank %d" % rank
             torch.cuda.synchronize()
             if eng.gather_timed_out():
                 status = "timeout"
@@ -80,9 +91,14 @@ def _worker(rank, world, port, f4, q):
         dist.destroy_process_group()
 
 
+def TILE_OK(b, b2):
+    return all(int(x) % 64 == 0 for x in b[:-1])
+
+
 @pytest.mark.timeout(300)
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["thread_stores", "copy_engines", "bulk_stores"])
 @pytest.mark.parametrize("f4", [False, True])
-def test_two_rank_fused_gather_over_ipc(f4):
+def test_two_rank_fused_gather_over_ipc(f4, mode):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
@@ -90,7 +106,7 @@ def test_two_rank_fused_gather_over_ipc(f4):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    ps = [ctx.Process(target=_worker, args=(r, 2, port, f4, q)) for r in range(2)]
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, f4, mode, q)) for r in range(2)]
     for p in ps:
         p.start()
     for p in ps:
