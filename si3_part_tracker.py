@@ -235,6 +235,8 @@ def main():
         """rank 0, whole rows in file order: append to the full-series file, remember the closing rows"""
         if writer is not None:
             writer.write(k + 1, vTime[k + 1], yx[:, 0], yx[:, 1], ll[:, 0], ll[:, 1], mask=m)
+        if not lUse2DTime:                                        # reference :376, live: the buoys this record advanced
+            print('   *   record ' + str(k + kstrt) + ': number of buoys alive = ' + str(int(np.count_nonzero(m))))
         sel = np.flatnonzero(kN == k + 1)
         z2XY[1, sel], z2GC[1, sel], zMSK[1, sel] = yx[sel], ll[sel], m[sel]
 
@@ -279,8 +281,9 @@ def main():
         dist.destroy_process_group()
         if rank != 0:
             return 0
-    for jt in range(Nt):
-        print('   *   record ' + str(jt + kstrt) + ': number of buoys alive = ' + str(int(n_alive[jt])))
+    if lUse2DTime:
+        for jt in range(Nt):
+            print('   *   record ' + str(jt + kstrt) + ': number of buoys alive = ' + str(int(n_alive[jt])))
 
     # ---- outputs (reference :498-571) ---------------------------------------------------------------
     if writer is not None:
