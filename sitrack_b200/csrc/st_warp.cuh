@@ -27,6 +27,7 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
     __shared__ int2 qC[NW][QCAP];
     __shared__ unsigned qI[NW][QCAP];
     __shared__ __align__(128) double2 sRow[ROWS ? NW : 1][ROWS ? 32 : 1];    // tile staging of the bulk peer stores
+
     bool bulk_pending = false;                                              // lane 0: a bulk group may still read sRow
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -35,16 +36,19 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
 
     auto load_state = [&](int tile, int8_t& al, pt& P, int2& c2) {
         const long long p = (long long)tile * 32 + lane;
-        al = 0; P.y = ST_FILL; P.x = ST_FILL; c2 = make_int2(2, 2);
+        P.y = ST_FILL; P.x = ST_FILL; c2 = make_int2(ST_DEAD_BIT | 2, 2);
         if (tile < ntiles && p < s.nP) {
-            al = __ldcs(s.alive + p);
             P = ld_stream_pt(s.pos + p);
-#ifdef ST_CELL_CG
-            c2 = __ldcg(s.cell + p);                              // evict-normal: the sector is still in L2 when a walk pass rewrites 8 bytes of it
-#else
-            c2 = __ldcs(s.cell + p);
-#endif
+            // evict-normal: the sector is still in L2 when a walk pass rewrites 8 bytes of it (a partial store into a
+            // sector that has left L2 costs a DRAM read-modify-write, profiles/README.md round 2)
+            c2 = __ldcg(s.cell + p);
         }
+#ifdef ST_ALIVE_BYTE
+        al = 0;
+        if (tile < ntiles && p < s.nP) al = __ldcs(s.alive + p);
+#else
+        al = (int8_t)(c2.x >= 0);                                 // bit 31 of jT = discontinued: `alive` is not read (24 B of state in)
+#endif
     };
     auto walk_pass = [&](int lo, int n) {
         __syncwarp();                                             // queue entries of this warp visible
@@ -66,11 +70,7 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
                 walk_cell(g, ic, A, B, cc.x, cc.y, a2);
                 const unsigned p = qI[wid][e];
                 if (!a2) cc.x |= ST_DEAD_BIT;
-#ifdef ST_CELL_CG
                 if (cc.x != j0 || cc.y != i0) __stcg(s.cell + p, cc);
-#else
-                if (cc.x != j0 || cc.y != i0) __stcs(s.cell + p, cc);
-#endif
                 if (!a2) s.alive[p] = 0;
             }
         }
