@@ -400,3 +400,45 @@ def test_cli_sort_flag_permutes_buoys_not_trajectories(tmp_path, monkeypatch):
         assert np.array_equal(res[False][0][k], res[True][0][k]), k
     for x, y in zip(res[False][1], res[True][1]):
         assert np.array_equal(x, y)
+
+
+def test_cloud_buoy_writer_streams_rows_to_npz(tmp_path):
+    """CloudBuoyWriter on the .npz backend: rows appended one at a time through on-disk members, the file assembled
+    at close with the variables and dtypes of ncSaveCloudBuoys, scratch directory gone, and identical to the
+    whole-array writer's file."""
+    import sitrack_b200 as sit
+    nt, nP = 5, 300
+    rng = np.random.default_rng(1)
+    t = 850608000 + 3600 * np.arange(nt)
+    ids = rng.permutation(nP) + 1
+    Y, X = rng.uniform(-900, 900, (nt, nP)), rng.uniform(-900, 900, (nt, nP))
+    La, Lo = rng.uniform(60, 90, (nt, nP)), rng.uniform(-180, 180, (nt, nP))
+    M = (rng.random((nt, nP)) > 0.2).astype("i1")
+    f1, f2 = str(tmp_path / "a.npz"), str(tmp_path / "b.npz")
+    with contextlib.redirect_stdout(io.StringIO()):
+        with sit.CloudBuoyWriter(f1, nt, ids, with_mask=True) as w:
+            for jt in range(nt):
+                w.write(jt, t[jt], Y[jt].astype("f4"), X[jt].astype("f4"), La[jt], Lo[jt], mask=M[jt])
+        sit.ncSaveCloudBuoys(f2, t, ids, Y, X, La, Lo, mask=M)
+    assert sorted(os.listdir(tmp_path)) == ["a.npz", "b.npz"]          # no scratch directory left behind
+    a, b = np.load(f1), np.load(f2)
+    assert sorted(a.files) == sorted(b.files) == sorted(["time", "buoy", "id_buoy", "latitude", "longitude", "y_pos", "x_pos", "mask"])
+    for k in a.files:
+        assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+    assert a["y_pos"].dtype == np.float32 and a["time"].dtype == np.int32 and a["id_buoy"].dtype == np.int64
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference on the small config: one JSON line with the keys the driver reads (no GPU involved)."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg2",
+                        "--steps", "2", "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=600)
+    assert r.returncode == 0
+    lines = [l for l in r.stdout.decode().splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "buoy-steps/sec" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["e2e"] == {"value": d["value"], "unit": "buoy-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "lat/lon" in d["cpu_baseline"]["sample"]
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["gpu_launches"] == 0

@@ -78,3 +78,22 @@ def test_two_rank_shard_and_gather():
     assert all(p.exitcode == 0 for p in ps), [p.exitcode for p in ps]
     status, n, lo, hi = q.get(timeout=5)
     assert status == "ok" and n > 512 and (lo, hi) == (0, 512)
+
+
+def test_shard_bounds_are_tile_aligned_and_balanced():
+    """Every rank's block starts on a tile boundary (a multiple of 32 rows is what the peer stores of the fused
+    all-gather need to cover whole sectors at the receiver) and the blocks differ by one tile at most."""
+    import numpy as np
+    from sitrack_b200.dist import shard_bounds, my_shard, TILE
+    assert TILE % 32 == 0
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n = int(rng.integers(0, 5_000_000)); world = int(rng.integers(1, 17)); tile = int(rng.choice([32, 64, 256]))
+        b = shard_bounds(n, world, tile)
+        assert b[0] == 0 and b[-1] == n and len(b) == world + 1 and np.all(np.diff(b) >= 0)
+        assert all(int(x) % tile == 0 for x in b[:-1] if x < n)
+        sizes = np.diff(b)
+        full = sizes[sizes > 0][:-1] if (sizes > 0).any() else sizes
+        assert full.size == 0 or full.max() - full.min() <= tile
+        r = int(rng.integers(0, world))
+        assert my_shard(n, r, world, tile) == (int(b[r]), int(b[r + 1]))
