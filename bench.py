@@ -230,7 +230,11 @@ def run_ours(args):
         eng.submit_record(r)
     torch.cuda.synchronize()
 
+    # the f8 row of record k is the position input of record k+1, as xPosC[jt] is in the reference: the two row buffers
+    # below alternate, so the previous row is intact while the next one is written (st_set_row_chain)
+    eng.set_row_chain(not args.no_chain)
     NB = 2
+    NBV = max(1, min(NB, args.row_buffers))          # row buffers of the value loop (1: the rows are stepped in place)
     o_yx = [torch.empty((nP, 2), dtype=torch.float64, device=dev) for _ in range(NB)]
     o_ll = [torch.empty((nP, 2), dtype=torch.float64, device=dev) for _ in range(NB)]
     o_mk = [torch.empty((nP,), dtype=torch.int8, device=dev) for _ in range(NB)]
@@ -253,7 +257,7 @@ def run_ours(args):
         reset(sort)
         na = torch.zeros((nwarm + nsteps,), dtype=torch.int64, device=dev)
         for k in range(nwarm):
-            b = k % NB
+            b = k % NBV
             eng.step(k % R, k, o_yx[b], ll_of(b), o_mk[b], na[k:k + 1], stream)
             if after_step:
                 after_step(k, b)
@@ -261,7 +265,7 @@ def run_ours(args):
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record(stream)
         for k in range(nwarm, nwarm + nsteps):
-            b = k % NB
+            b = k % NBV
             eng.step(k % R, k, o_yx[b], ll_of(b), o_mk[b], na[k:k + 1], stream)
             if after_step:
                 after_step(k, b)
@@ -293,9 +297,15 @@ def run_ours(args):
     # roofline of the dominant kernel on THIS rank: algorithmic bytes / its mean launch duration.
     # The K launches run back to back on one stream, so the event span / K is the launch duration.
     achieved = (bsteps / K) * B_ALG / (ms / K * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_advect_step_v1<1,false>" if args.kernel == "v1" else ("k_advect_warp<1,false,0,1,32,32>" if args.kernel == "tuned" else "step variant %s" % args.kernel), "achieved": round(achieved, 1), "peak": peak,
+    MOVED = 58.0 if (not args.no_chain and args.kernel in ("tuned", "0", "2", "3", "5")) else 74.0
+    roof = {"bound": "hbm", "kernel": "k_advect_step_v1<1,false>" if args.kernel == "v1" else (("k_advect_warp<1,false,0,1,32,32>" if args.no_chain else "k_advect_warp<1,false,2,1,32,32>") if args.kernel == "tuned" else "step variant %s" % args.kernel), "achieved": round(achieved, 1), "peak": peak,
             "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload),
             "peak_source": peak_src, "alg_bytes_per_buoy_step": B_ALG,
+            # what this build moves per buoy-step: 24 B of state in (position, cell; the alive flag is bit 31 of the cell
+            # word), the 33 B row, ~1 B of cell rewrites (13 % of the buoys change cell) and, without row chaining, the
+            # 16 B position write-back of the state; `frac` stays on SURVEY 8(d)'s 83 B
+            "moved_bytes_per_buoy_step": MOVED,
+            "frac_of_moved_bytes": round(achieved / B_ALG * MOVED / peak, 4),
             "buoy_steps_per_launch": bsteps / K, "us_per_launch": round(ms / K * 1e3, 2)}
 
     extra = {}
@@ -550,6 +560,8 @@ def run_ours(args):
                                 % (nP * B_ALG / 1e6, R, R * 3 * Nj * Ni * 4 / 1e6),
                           "input_order": "as generated (cell-major)" if args.no_shuffle else
                                          "random (shuffled); stored cell-major by the product (set_buoys sort)",
+                          "state": "separate position state, rewritten every record" if args.no_chain else
+                                   "positions chained through the f8 trajectory rows (st_set_row_chain)",
                           "parallelism": "buoys sharded over %d GPU(s), record replicated" % world},
                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
                "clocks": clocks, "seed_locate": {"buoys_per_s": SC_t.shape[0] / (seed_ms * 1e-3), "ms": round(seed_ms, 3)}}
@@ -753,6 +765,8 @@ def main():
     ap.add_argument("--no-allgather", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="strong: the workload's buoy count is the TOTAL, sharded over the ranks (config 4: --workload cfg4)")
+    ap.add_argument("--row-buffers", type=int, default=2, help="device row buffers the value loop cycles through (1: rows stepped in place)")
+    ap.add_argument("--no-chain", action="store_true", help="A/B: keep a separate position state (st_set_row_chain off)")
     ap.add_argument("--no-shuffle", action="store_true", help="diagnostic: feed the seeds in generator (cell-major) order, no sort")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2000, help="buoys in the Python cpu_baseline sample")

@@ -35,7 +35,7 @@ extern "C" {
 #define ST_ESTATE   -3      /* call order (e.g. step before set_buoys)   */
 #define ST_ENOMEM   -4
 
-#define ST_ABI_VERSION 2
+#define ST_ABI_VERSION 3
 
 typedef struct st_ctx st_ctx;
 
@@ -123,6 +123,20 @@ int  st_set_buoys_dev(st_ctx *ctx, int64_t nP, const double *pos_dev, const int3
 int  st_get_state(st_ctx *ctx, double *pos, int32_t *cell, int8_t *alive);          /* host out, syncs */
 int  st_state_device_ptrs(st_ctx *ctx, double **pos_dev, int32_t **cell_dev, int8_t **alive_dev);
 int64_t st_num_buoys(const st_ctx *ctx);
+/* Row chaining (off by default).  The reference keeps no separate position state: xPosC[jt] IS the
+ * input of iteration jt and xPosC[jt+1] its output (si3_part_tracker.py:412,459-460).  With chaining
+ * on, st_step does the same on the device: it reads the positions of the buoys that are alive from
+ * the f8 out_yx_dev row of the PREVIOUS st_step (from the state on the first one) and stores the new
+ * ones into the new row only -- 16 B per buoy-step less to write.  The caller promises that a row
+ * handed to st_step stays intact until the next st_step on the same stream has run (the next step
+ * may write into the same buffer: every buoy is read before it is written, by the same thread).  A
+ * step that cannot chain (f4 rows, out_yx_dev NULL, per-buoy record windows, st_step_multi / _ext /
+ * _gather, kernel variants 1 and 4) first brings the state up to date and then runs as without
+ * chaining; so do st_get_state, st_state_device_ptrs (which then synchronise the device) and
+ * st_set_row_chain(ctx, 0).  st_sync_state does it explicitly (ASYNC on `stream`), e.g. before the
+ * last row buffer is released.  Results are bit-identical with and without chaining.             */
+int  st_set_row_chain(st_ctx *ctx, int on);
+int  st_sync_state(st_ctx *ctx, void *stream);
 
 /* ---- hourly records (xUu, xVv, xIC; si3_part_tracker.py:372-374) ----------------------
  * A slot holds one record as three contiguous (Nj,Ni) f4 planes [u_ice | v_ice |

@@ -48,6 +48,8 @@ SIGNATURES = {
     "st_set_buoys_dev": (c_int, [vp, c_i64, vp, vp, vp, vp, vp]),
     "st_get_state": (c_int, [vp, vp, vp, vp]),
     "st_state_device_ptrs": (c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "st_set_row_chain": (c_int, [vp, c_int]),
+    "st_sync_state": (c_int, [vp, vp]),
     "st_num_buoys": (c_i64, [vp]),
     "st_record_slots": (c_int, [vp, c_int]),
     "st_record_host_buffer": (c_int, [vp, c_int, C.POINTER(vp)]),
@@ -95,7 +97,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             f = getattr(L, name)
             f.restype, f.argtypes = res, args
-        if L.st_abi_version() != 2:
+        if L.st_abi_version() != 3:
             raise SitrackCudaError("libsitrack_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -42,6 +42,10 @@ struct st_ctx {
     int32_t *rec_first = nullptr, *rec_last = nullptr;
     bool has_window = false;
     int variant = 0;            // st_set_kernel_variant: 0 = k_advect_warp (default), 1 = k_advect_step_v1, ...
+    // row chaining (st_set_row_chain): pos_src != nullptr => the positions of the buoys that are alive live in that
+    // f8 yx row (the last chained step's), pos holds them only for the discontinued ones until sync_pos()
+    bool chain_on = false;
+    const pt* pos_src = nullptr;
     // host-API scratch outputs
     pt *o_yx = nullptr, *o_ll = nullptr; int8_t* o_mask = nullptr; unsigned long long* o_nalive = nullptr;
     long long capOut = 0;
@@ -65,6 +69,7 @@ struct st_ctx {
 };
 
 static thread_local std::string g_err;
+extern "C" { static int sync_pos_blocking(st_ctx* c); }      // row chaining: defined with the step
 
 static int fail(st_ctx* c, int code, const std::string& msg)
 {
@@ -332,13 +337,13 @@ static int ensure_walk_scratch(st_ctx* c)
 int st_set_kernel_variant(st_ctx* c, int variant)
 {
 #ifdef ST_EXPERIMENTS
-    const bool known = variant >= 0 && variant <= 12 && variant != 5;
+    const bool known = variant >= 0 && variant <= 12;
 #else
-    const bool known = variant >= 0 && variant <= 4;
+    const bool known = variant >= 0 && variant <= 5;
 #endif
-    if (!c || !known) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 = 2 warp-private with orientation filter (default), 1 v1, 3 warp-private exact, 4 certified two-kernel step; 6-12 only in -DST_EXPERIMENTS builds");
+    if (!c || !known) return fail(c, ST_EINVAL, "st_set_kernel_variant: 0 = 2 warp-private with orientation filter (default), 1 v1, 3 warp-private exact, 4 certified two-kernel step, 5 default kernel with the certified U/V pick; 6-12 only in -DST_EXPERIMENTS builds");
     // a grid that does not qualify for frames (st_create: filter_ok) runs variant 4 as variant 2
-    if (variant == 4 && c->grid.filter_ok) { int rc = ensure_frames(c); if (rc) return rc; }
+    if ((variant == 4 || variant == 5) && c->grid.filter_ok) { int rc = ensure_frames(c); if (rc) return rc; }
     c->variant = variant;
     return ST_OK;
 }
@@ -570,6 +575,7 @@ static int set_buoys_impl(st_ctx* c, int64_t nP, const double* pos, const int32_
     if ((rf == nullptr) != (rl == nullptr)) return fail(c, ST_EINVAL, "st_set_buoys: rec_first and rec_last go together");
     CU(c, cudaSetDevice(c->device));
     c->nP = 0;
+    c->pos_src = nullptr;                                         // a new cloud: nothing to carry over from a chained row
     if (nP > 0) {
         int rc = reserve_buoys(c, nP, rf != nullptr, s);
         if (rc) return rc;
@@ -609,6 +615,7 @@ int st_get_state(st_ctx* c, double* pos, int32_t* cell, int8_t* alive)
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaDeviceSynchronize());
     if (c->nP == 0) return ST_OK;
+    { int rs = sync_pos_blocking(c); if (rs) return rs; }
     if (pos) CU(c, cudaMemcpy(pos, c->pos, sizeof(pt) * c->nP, cudaMemcpyDeviceToHost));
     if (cell) {
         CU(c, cudaMemcpy(cell, c->cell, sizeof(int2) * c->nP, cudaMemcpyDeviceToHost));
@@ -621,6 +628,7 @@ int st_get_state(st_ctx* c, double* pos, int32_t* cell, int8_t* alive)
 int st_state_device_ptrs(st_ctx* c, double** pos, int32_t** cell, int8_t** alive)
 {
     if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    { int rs = sync_pos_blocking(c); if (rs) return rs; }          // after chained steps: synchronises the device
     if (pos) *pos = (double*)c->pos;
     if (cell) *cell = (int32_t*)c->cell;
     if (alive) *alive = c->alive;
@@ -692,7 +700,51 @@ static BuoyState state_of(st_ctx* c)
     s.rec_first = c->has_window ? c->rec_first : nullptr;
     s.rec_last = c->has_window ? c->rec_last : nullptr;
     s.q = c->wq;
+    s.pos_in = nullptr; s.chain = 0;
     return s;
+}
+
+// st_sync_state: pos <- the chained row for every buoy that is alive; everything that reads pos other than a chained
+// step comes through here first
+__global__ void k_sync_pos(long long nP, const pt* __restrict__ row, const int2* __restrict__ cell, pt* __restrict__ pos)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < nP && cell[p].x >= 0) pos[p] = row[p];
+}
+static int sync_pos(st_ctx* c, cudaStream_t s)
+{
+    if (!c->pos_src) return ST_OK;
+    if (c->nP > 0) {
+        k_sync_pos<<<(unsigned)((c->nP + 255) / 256), 256, 0, s>>>(c->nP, c->pos_src, c->cell, c->pos);
+        CU(c, cudaGetLastError());
+    }
+    c->pos_src = nullptr;
+    return ST_OK;
+}
+// the same for the synchronous entry points: work the caller queued on any stream finishes first
+static int sync_pos_blocking(st_ctx* c)
+{
+    if (!c->pos_src) return ST_OK;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    int rc = sync_pos(c, c->stream); if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return ST_OK;
+}
+
+int st_set_row_chain(st_ctx* c, int on)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    if (!on) { int rc = sync_pos_blocking(c); if (rc) return rc; }
+    c->chain_on = on != 0;
+    return ST_OK;
+}
+
+int st_sync_state(st_ctx* c, void* stream)
+{
+    if (!c) return fail(nullptr, ST_EINVAL, "ctx is NULL");
+    CU(c, cudaSetDevice(c->device));
+    return sync_pos(c, (cudaStream_t)stream);
 }
 
 static int step_impl(st_ctx* c, int slot, int jrec, void* out_yx, void* out_latlon, int8_t* out_mask,
@@ -705,7 +757,14 @@ static int step_impl(st_ctx* c, int slot, int jrec, void* out_yx, void* out_latl
     StepOut o{(pt*)out_yx, (pt*)out_latlon, out_mask, (unsigned long long*)n_alive};
     o.f4 = f4;
     if (c->variant == 4) { int rs = ensure_walk_scratch(c); if (rs) return rs; }
-    CU(c, launch_advect_step(c->grid, r, r + npt, r + 2 * npt, state_of(c), jrec, o, c->variant, (cudaStream_t)stream));
+    BuoyState s = state_of(c);
+    // a chained step: f8 rows on this device, every buoy in its window, a kernel of the k_advect_warp family
+    const int v = c->variant;
+    const bool chain = c->chain_on && !f4 && out_yx && !c->has_window && c->nP > 0 && (v == 0 || v == 2 || v == 3 || v == 5);
+    if (chain) { s.pos_in = c->pos_src ? c->pos_src : c->pos; s.chain = 1; }
+    else       { int rs = sync_pos(c, (cudaStream_t)stream); if (rs) return rs; }
+    CU(c, launch_advect_step(c->grid, r, r + npt, r + 2 * npt, s, jrec, o, c->variant, (cudaStream_t)stream));
+    if (chain) c->pos_src = (const pt*)out_yx;
     return ST_OK;
 }
 
@@ -733,6 +792,7 @@ int st_step_ext(st_ctx* c, int slot, int jrec, int scheme, int interp, int max_h
     const size_t npt = (size_t)c->Nj * c->Ni;
     const float* r = c->d_rec[slot];
     StepOut o{(pt*)out_yx, (pt*)out_latlon, out_mask, (unsigned long long*)n_alive};
+    { int rs = sync_pos(c, (cudaStream_t)stream); if (rs) return rs; }
     CU(c, launch_advect_ext(c->grid, r, r + npt, r + 2 * npt, state_of(c), jrec, o, scheme, interp, max_hops,
                             (cudaStream_t)stream));
     return ST_OK;
@@ -749,6 +809,7 @@ static int step_multi_impl(st_ctx* c, const float* rec_dev, int64_t rec_stride, 
     CU(c, cudaSetDevice(c->device));
     StepOut o{(pt*)out_yx, (pt*)out_latlon, out_mask, (unsigned long long*)n_alive};
     o.f4 = f4;
+    { int rs = sync_pos(c, (cudaStream_t)stream); if (rs) return rs; }
     CU(c, launch_advect_multi(c->grid, rec_dev, rec_stride, nrec, state_of(c), jrec0, o, out_stride, (cudaStream_t)stream));
     return ST_OK;
 }
@@ -929,6 +990,7 @@ int st_step_gather(st_ctx* c, int slot, int jrec, int buf, uint64_t seq, void* o
     o.npeer = 0;
     o.bulk = 0;
     if (c->variant == 4) { int rs = ensure_walk_scratch(c); if (rs) return rs; }
+    { int rs = sync_pos(c, (cudaStream_t)stream); if (rs) return rs; }
     if (g.mode == 1 && g.world > 1) {
         // copy engines: the kernel writes this rank's block only; one peer-to-peer copy per peer follows on its own
         // stream, and the ready flags are released from a side stream once all of them have landed -- the caller's
@@ -1048,6 +1110,7 @@ static int track_record_host_impl(st_ctx* c, int jrec, const float* u, const flo
     o.f4 = f4;
     const size_t rowb = f4 ? sizeof(float2) : sizeof(pt);
     if (c->variant == 4) { int rs = ensure_walk_scratch(c); if (rs) return rs; }
+    { int rs = sync_pos_blocking(c); if (rs) return rs; }
     CU(c, launch_advect_step(c->grid, d, d + npt, d + 2 * npt, state_of(c), jrec, o, c->variant, s));
     if (c->nP > 0) {
         if (out_yx) CU(c, cudaMemcpyAsync(out_yx, c->o_yx, rowb * c->nP, cudaMemcpyDeviceToHost, s));

@@ -45,6 +45,12 @@ struct BuoyState {
     const int32_t* rec_first;   // optional per-buoy record window (no -F); nullptr with -F
     const int32_t* rec_last;
     WalkScratch q;              // q.P == nullptr: not allocated (variant 2 runs instead of the default step)
+    // Row chaining (st_set_row_chain, k_advect_warp ROWS 2): the f8 yx row of the previous step IS the position
+    // state of the buoys that are alive.  The step reads positions from pos_in (that row, or pos on the first
+    // step) and stores the new ones into the new row only -- pos is written at a buoy's death (its last position)
+    // and by st_sync_state.  16 B per buoy-step less to write.
+    const pt* pos_in;           // nullptr: pos
+    int chain;                  // 1: this launch leaves pos alone (set by the API layer only when the launch qualifies)
 };
 
 // One trajectory row (all nullable).

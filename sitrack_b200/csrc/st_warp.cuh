@@ -10,12 +10,24 @@
 //     certifies "inside" for lanes clear of every edge; the others are queued and the dense pass applies the
 //     reference's own test before walking -- the exact test runs on ~15 % of the buoys instead of all;
 //   * the row-store mode is a template parameter (ROWS 0: f8 rows into local HBM; 1: f4 rows and/or
-//     remote rows of the fused all-gather), so the default path carries no per-row mode branches.
+//     remote rows of the fused all-gather; 2: f8 rows that are also the position state, see BuoyState::pos_in),
+//     so the default path carries no per-row mode branches.
 // Arithmetic, store addresses and results are those of k_advect_persist / k_advect_step_v1, bit for bit.
 #pragma once
 #include "st_kernels.h"
 
 namespace st {
+
+// FILT 2 (variant 5): as FILT 1, and the U/V pick of the common path comes from the cell's certified frame
+// (st_cert.cuh: k_cell_frames proves per cell that msep < |s|,|t| < hin  =>  llum1 = (s < 0), llvm1 = (t < 0)); the
+// four U/V-point gathers and the two segment tests then run only for the ~1 % of lanes that are not certified.
+__device__ __forceinline__ float4 ldg_frame(const float4* a)
+{
+    float4 r;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(a), "l"(l2_keep_policy()));
+    return r;
+}
 
 template <int UV, bool WIN, int ROWS, int FILT, int BLK, int MINB>
 __global__ void __launch_bounds__(BLK, MINB)
@@ -23,10 +35,13 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
               const float* __restrict__ ic, BuoyState s, int jrec, StepOut o, int ntiles)
 {
     constexpr int NW = BLK / 32, QCAP = 64;
+    constexpr bool PEER = ROWS == 1, CHAIN = ROWS == 2;
+    static_assert(!(CHAIN && WIN), "a buoy outside its record window has a fill row but a live position");
+    const pt* __restrict__ pos_in = CHAIN ? s.pos_in : s.pos;
     __shared__ pt qP[NW][QCAP], qPn[NW][QCAP];
     __shared__ int2 qC[NW][QCAP];
     __shared__ unsigned qI[NW][QCAP];
-    __shared__ __align__(128) double2 sRow[ROWS ? NW : 1][ROWS ? 32 : 1];    // tile staging of the bulk peer stores
+    __shared__ __align__(128) double2 sRow[PEER ? NW : 1][PEER ? 32 : 1];    // tile staging of the bulk peer stores
 
     bool bulk_pending = false;                                              // lane 0: a bulk group may still read sRow
 
@@ -38,7 +53,7 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
         const long long p = (long long)tile * 32 + lane;
         P.y = ST_FILL; P.x = ST_FILL; c2 = make_int2(ST_DEAD_BIT | 2, 2);
         if (tile < ntiles && p < s.nP) {
-            P = ld_stream_pt(s.pos + p);
+            P = ld_stream_pt(pos_in + p);
             // evict-normal: the sector is still in L2 when a walk pass rewrites 8 bytes of it (a partial store into a
             // sector that has left L2 costs a DRAM read-modify-write, profiles/README.md round 2)
             c2 = __ldcg(s.cell + p);
@@ -72,6 +87,7 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
                 if (!a2) cc.x |= ST_DEAD_BIT;
                 if (cc.x != j0 || cc.y != i0) __stcg(s.cell + p, cc);
                 if (!a2) s.alive[p] = 0;
+                if (CHAIN && !a2) st_stream_pt(s.pos + p, B);     // the rows from here on hold the fill value
             }
         }
         __syncwarp();                                             // slots may be overwritten again
@@ -103,7 +119,35 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
         const pt bl = ldg_pt(g.F, c - Ni - 1), br = ldg_pt(g.F, c - Ni);
         const pt ul = ldg_pt(g.F, c - 1),      ur = ldg_pt(g.F, c);
         double zU, zV;
-        if (UV == 1) {
+        bool convex = true;                                       // FILT 2: bit 2 of the cell's orientation bits
+        if (UV == 1 && FILT == 2) {
+            const float4 f0 = ldg_frame(g.frames + 2 * (size_t)c), f1 = ldg_frame(g.frames + 2 * (size_t)c + 1);
+            const float uL = __ldg(u + c - 1), uR = __ldg(u + c);
+            const float vB = __ldg(v + c - Ni), vT = __ldg(v + c);
+            // frame coordinates of P (st_cert.cuh: cert_eval): f0 = {oy, ox, a, b}, f1 = {c, d, hin|msep, es|et}
+            const unsigned mw = __float_as_uint(f1.z), ew = __float_as_uint(f1.w);
+            const float hin = __uint_as_float(mw & 0xffff0000u), msep = __uint_as_float(mw << 16);
+            const float fy = __double2float_rn(__dsub_rn(P.y, (double)f0.x));
+            const float fx = __double2float_rn(__dsub_rn(P.x, (double)f0.y));
+            const float fs = __fmaf_rn(f0.z, fx, __fmaf_rn(f0.w, fy, __uint_as_float(ew & 0xffff0000u)));
+            const float ft = __fmaf_rn(f1.x, fx, __fmaf_rn(f1.y, fy, __uint_as_float(ew << 16)));
+            const float as = fabsf(fs), at = fabsf(ft);
+            const bool pick_ok = (as < hin) & (at < hin) & (as > msep) & (at > msep);   // an admitted cell is convex (bit 2)
+            bool llum1 = fs < 0.0f, llvm1 = ft < 0.0f;            // si3_part_tracker.py:430-431 when certified
+            const bool need = active && !pick_ok;
+            if (__any_sync(0xffffffffu, need)) {                  // the reference's own segment tests for the others
+                if (need) {
+                    const pt v0 = ldg_pt(g.V, c - Ni), v1 = ldg_pt(g.V, c);
+                    const pt u0 = ldg_pt(g.U, c - 1),  u1 = ldg_pt(g.U, c);
+                    const int cb = __ldg(g.cellbits + c);
+                    llum1 = intersect2seg_pre(P, ur, v0, v1, cb & 1);
+                    llvm1 = intersect2seg_pre(P, ur, u0, u1, cb & 2);
+                    convex = (cb & 4) != 0;
+                }
+            }
+            zU = (double)(llum1 ? uL : uR);
+            zV = (double)(llvm1 ? vB : vT);
+        } else if (UV == 1) {
             const pt v0 = ldg_pt(g.V, c - Ni), v1 = ldg_pt(g.V, c);
             const pt u0 = ldg_pt(g.U, c - 1),  u1 = ldg_pt(g.U, c);
             const float uL = __ldg(u + c - 1), uR = __ldg(u + c);
@@ -121,19 +165,20 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
         Pn.x = __dadd_rn(P.x, div1000(__dmul_rn(zU, g.rdt)));      // :452-458
         Pn.y = __dadd_rn(P.y, div1000(__dmul_rn(zV, g.rdt)));
         bool in;
-        if (FILT) in = inside_margin(Pn.y, Pn.x, bl, br, ur, ul) && (__ldg(g.cellbits + c) & 4);   // same byte as the pick's
+        if (FILT == 2 && UV == 1) in = inside_margin(Pn.y, Pn.x, bl, br, ur, ul) && convex;
+        else if (FILT) in = inside_margin(Pn.y, Pn.x, bl, br, ur, ul) && (__ldg(g.cellbits + c) & 4);   // same byte as the pick's
         else      in = inside_quad2(Pn.y, Pn.x, bl, br, ur, ul, active);
         const bool cross = active && !in;
         pt outp = {ST_FILL, ST_FILL};
         int8_t m = 0;
         if (active) {
             outp = Pn; m = 1;
-            st_stream_pt(s.pos + p, outp);
+            if (!CHAIN) st_stream_pt(s.pos + p, outp);
         } else if (WIN && prestart) {
             outp = P; m = 1;
         }
         if (valid) {
-            if (ROWS == 0) {
+            if (!PEER) {
                 if (o.yx) st_stream_pt(o.yx + p, outp);
             } else if (o.bulk && (long long)tile * 32 + 32 <= s.nP) {      // warp-uniform: a full tile
                 // own block: plain row store; peers: the tile goes through shared memory and one bulk copy per peer
@@ -166,7 +211,7 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
             if (o.latlon) {
                 pt ll; ll.y = g.proj.fill_lat; ll.x = g.proj.fill_lon;            // :493 on a fill row
                 if (m) ll = inv_stere_fast(outp, g.proj, g.atab);
-                if (ROWS == 0) st_stream_pt(o.latlon + p, ll);
+                if (!PEER) st_stream_pt(o.latlon + p, ll);
                 else           put_row_pt(o.latlon, p, ll, o.f4);
             }
         }
@@ -185,7 +230,7 @@ k_advect_warp(const AdvectGrid g, const float* __restrict__ u, const float* __re
         }
         al = nal; P = nP_; c2 = nc2;
     }
-    if (ROWS && lane == 0 && bulk_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the peers' rows have left
+    if (PEER && lane == 0 && bulk_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the peers' rows have left
     walk_pass(0, qn);                                             // flush (qn < 32)
     if (o.n_alive) {
         const int wsum = __reduce_add_sync(0xffffffffu, my_alive);

@@ -282,6 +282,16 @@ class TrackEngine:
             return tuple(out)
         return pos, cell, alive
 
+    def set_row_chain(self, on=True):
+        """Row chaining (st_set_row_chain): the f8 yx row of a step is the position input of the next one, as
+        xPosC[jt] is in the reference (si3_part_tracker.py:412,459-460); the state's own copy is not rewritten every
+        record.  The caller keeps each row intact until the next step has run."""
+        check(self.L.st_set_row_chain(self.h, 1 if on else 0), self.h)
+
+    def sync_state(self, stream=None):
+        """Bring the position state up to date after chained steps (async on `stream`)."""
+        check(self.L.st_sync_state(self.h, _sptr(stream)), self.h)
+
     # -- records -----------------------------------------------------------------------
     def record_slots(self, n):
         check(self.L.st_record_slots(self.h, int(n)), self.h)
@@ -489,39 +499,48 @@ class TrackEngine:
             stg[b][0], stg[b][1], stg[b][2] = u, v, ic     # f4 copy into pinned memory
         pool = ThreadPoolExecutor(1)
         nxt = pool.submit(load, 0) if nrec > 0 else None
-        for k in range(nrec):
-            b = k % 2
-            nxt.result()
-            if k + 1 < nrec:
-                nxt = pool.submit(load, k + 1)             # waits for ev_in[k-1], recorded below before it can matter
-            if k >= 2:
-                s_in.wait_event(ev_step[k - 2])            # device slot b no longer read
-            self.submit_record(b, s_in)
-            ev_in[k] = torch.cuda.Event(); ev_in[k].record(s_in)
-            s_cmp.wait_event(ev_in[k])
-            if k >= NB:
-                s_cmp.wait_event(ev_out[k - NB])           # device out buffer b drained
-            if physics:
-                self.step_ext(b, k + kstrt, physics.get("scheme", 1), physics.get("interp", 0),
-                              physics.get("max_hops", 1), d_yx[b], d_ll[b], d_mk[b], d_na[k:k + 1], s_cmp)
-            else:
-                self.step(b, k + kstrt, d_yx[b], d_ll[b], d_mk[b], d_na[k:k + 1], s_cmp)
-            ev_step[k] = torch.cuda.Event(); ev_step[k].record(s_cmp)
-            s_out.wait_event(ev_step[k])
-            if not keep and k >= NB:
-                drain(k - NB)                              # pinned row buffer b is free again
-            y, l, m = rows(k)
-            with torch.cuda.stream(s_out):
-                y.copy_(d_yx[b], non_blocking=True)
-                if want_latlon:
-                    l.copy_(d_ll[b], non_blocking=True)
-                m.copy_(d_mk[b], non_blocking=True)
-            ev_out[k] = torch.cuda.Event(); ev_out[k].record(s_out)
-        for k in range(max(0, nrec - NB), nrec):
-            if keep:
-                ev_out[k].synchronize()
-            else:
-                drain(k)
+        # f8 rows: the row of record k is the position input of record k+1 (st_set_row_chain); both row buffers
+        # live until the chain is closed below
+        chain = rdt == torch.float64 and not physics
+        if chain:
+            self.set_row_chain(True)
+        try:
+            for k in range(nrec):
+                b = k % 2
+                nxt.result()
+                if k + 1 < nrec:
+                    nxt = pool.submit(load, k + 1)             # waits for ev_in[k-1], recorded below before it can matter
+                if k >= 2:
+                    s_in.wait_event(ev_step[k - 2])            # device slot b no longer read
+                self.submit_record(b, s_in)
+                ev_in[k] = torch.cuda.Event(); ev_in[k].record(s_in)
+                s_cmp.wait_event(ev_in[k])
+                if k >= NB:
+                    s_cmp.wait_event(ev_out[k - NB])           # device out buffer b drained
+                if physics:
+                    self.step_ext(b, k + kstrt, physics.get("scheme", 1), physics.get("interp", 0),
+                                  physics.get("max_hops", 1), d_yx[b], d_ll[b], d_mk[b], d_na[k:k + 1], s_cmp)
+                else:
+                    self.step(b, k + kstrt, d_yx[b], d_ll[b], d_mk[b], d_na[k:k + 1], s_cmp)
+                ev_step[k] = torch.cuda.Event(); ev_step[k].record(s_cmp)
+                s_out.wait_event(ev_step[k])
+                if not keep and k >= NB:
+                    drain(k - NB)                              # pinned row buffer b is free again
+                y, l, m = rows(k)
+                with torch.cuda.stream(s_out):
+                    y.copy_(d_yx[b], non_blocking=True)
+                    if want_latlon:
+                        l.copy_(d_ll[b], non_blocking=True)
+                    m.copy_(d_mk[b], non_blocking=True)
+                ev_out[k] = torch.cuda.Event(); ev_out[k].record(s_out)
+            for k in range(max(0, nrec - NB), nrec):
+                if keep:
+                    ev_out[k].synchronize()
+                else:
+                    drain(k)
+        finally:
+            if chain:
+                self.set_row_chain(False)                  # state up to date again (synchronises)
         torch.cuda.synchronize(dev)
         pool.shutdown()
         n_alive = d_na.cpu().numpy()

@@ -33,7 +33,7 @@ def test_header_symbols_exported(so):
 def test_binding_covers_header(so):
     from sitrack_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
-    assert _lib.lib().st_abi_version() == 2
+    assert _lib.lib().st_abi_version() == 3
 
 
 def test_only_sm100a_code(so):

@@ -183,7 +183,7 @@ def test_cert_step_vs_default_at_size(torch):
     rng = np.random.default_rng(11)
     rep = int(np.ceil(400_000 / SC.shape[0]))
     res = {}
-    for variant in (0, 4):
+    for variant in (0, 4, 5):
         with engine_for(g) as eng:
             eng.set_locate_grid(g["latT"], g["lonT"], g["ResKM"])
             cell, near, keep = eng.seed_locate(SG, SC, IC[0])
@@ -197,6 +197,10 @@ def test_cert_step_vs_default_at_size(torch):
             r = eng.track((U, V, IC), nrec, pos0=pos0)
             res[variant] = (r, eng.get_state())
     r0, s0 = res[0]; r4, s4 = res[4]
+    for k in ("posC", "mask", "n_alive"):
+        assert np.array_equal(r0[k], res[5][0][k]), k
+    for a, b in zip(s0, res[5][1]):
+        assert np.array_equal(a, b)
     assert np.array_equal(r0["posC"], r4["posC"]) and np.array_equal(r0["mask"], r4["mask"])
     assert np.array_equal(r0["n_alive"], r4["n_alive"])
     assert np.abs(r0["posG"][1:] - r4["posG"][1:]).max() == 0.0

@@ -118,7 +118,7 @@ def test_track_golden(torch, corc, gold_track, name, multi):
     assert np.abs(ll - want).max() < LATLON_TOL_DEG                  # also for the -9999 rows (:493)
 
 
-@pytest.mark.parametrize("variant", [1, 3, 4])
+@pytest.mark.parametrize("variant", [1, 3, 4, 5])
 @pytest.mark.parametrize("name", list(TRACK_CASES))
 def test_track_golden_other_kernels(torch, corc, gold_track, name, variant):
     """v1 (straightforward) and the round-1 default (k_advect_warp with and without the orientation filter)
@@ -136,6 +136,75 @@ def test_track_golden_other_kernels(torch, corc, gold_track, name, variant):
     assert np.array_equal(cells, T[name + "_jiT"]) and np.array_equal(alive, T[name + "_alive"])
     want = corc.inv_stere(T[name + "_posC"][1:].reshape(-1, 2)).reshape(ll.shape)
     assert np.abs(ll - want).max() < LATLON_TOL_DEG                  # every launch shape writes the same xPosG row
+
+
+@pytest.mark.parametrize("variant", [0, 3, 5])
+@pytest.mark.parametrize("name", list(TRACK_CASES))
+def test_row_chain_golden(torch, gold_track, name, variant):
+    """Row chaining (st_set_row_chain): the f8 row of record k is the position input of record k+1 and the state's
+    own copy is rewritten only at a buoy's death and by st_sync_state.  Rows, masks, alive counts, cells and the
+    final positions (discontinued buoys included) equal the golden run / the un-chained state bit for bit, whichever
+    way the caller lays out its rows: one row per record, two alternating buffers, ONE buffer stepped in place, a
+    state read-back after every record, and steps that cannot chain (no yx row, f4 rows) in between.  The windowed
+    case never chains (a buoy outside its window has a fill row but a live position) and must be unaffected."""
+    T, g = gold_track
+    c = TRACK_CASES[name]
+    sc = np.float32(c["scale"])
+    U, V, IC = sc * T["U"], sc * T["V"], T["IC"]
+    first = T["win_first"] if c["win"] else None
+    last = T["win_last"] if c["win"] else None
+    nrec, nP = U.shape[0], T["pos0"].shape[0]
+    dev = torch.device("cuda", 0)
+    want_yx, want_mk = T[name + "_posC"][1:], T[name + "_mask"][1:]
+    with engine_for(g, uv_strategy=c["uv_strategy"]) as eng:
+        eng.set_kernel_variant(variant)
+        eng.record_slots(1)
+
+        def run(mode):
+            eng.set_buoys(T["pos0"], T["jiT0"], first, last)
+            eng.set_row_chain(mode != "off")
+            nb = {"rows": nrec, "off": nrec, "sync_each": nrec, "mixed": nrec, "pingpong": 2, "inplace": 1}[mode]
+            yx = torch.full((nb, nP, 2), 7.0, dtype=torch.float64, device=dev)
+            yx4 = torch.empty((nP, 2), dtype=torch.float32, device=dev)
+            mk = torch.empty((nrec, nP), dtype=torch.int8, device=dev)
+            na = torch.zeros((nrec,), dtype=torch.int64, device=dev)
+            rows = np.full((nrec, nP, 2), np.nan)
+            for k in range(nrec):
+                st = eng.staging(0)
+                st[0], st[1], st[2] = U[k], V[k], IC[k]
+                eng.submit_record(0)
+                if mode == "mixed" and k % 3 == 1:
+                    eng.step(0, k + c["kstrt"], None, None, mk[k], na[k:k + 1])        # no row: cannot chain
+                elif mode == "mixed" and k % 3 == 2:
+                    eng.step(0, k + c["kstrt"], yx4, None, mk[k], na[k:k + 1])         # f4 row: cannot chain
+                    torch.cuda.synchronize()
+                    rows[k] = yx4.cpu().numpy().astype(np.float64)
+                else:
+                    eng.step(0, k + c["kstrt"], yx[k % nb], None, mk[k], na[k:k + 1])
+                    torch.cuda.synchronize()
+                    rows[k] = yx[k % nb].cpu().numpy()
+                if mode == "sync_each":
+                    _, cc, aa = eng.get_state()
+                    assert np.array_equal(cc, T[name + "_jiT"][k + 1]) and np.array_equal(aa, T[name + "_alive"][k + 1])
+            state = eng.get_state()
+            eng.set_row_chain(False)
+            return rows, mk.cpu().numpy(), na.cpu().numpy(), state
+
+        rows0, mk0, na0, st0 = run("off")
+        assert np.array_equal(rows0, want_yx) and np.array_equal(mk0, want_mk) and np.array_equal(na0, T[name + "_nalive"])
+        assert np.array_equal(st0[1], T[name + "_jiT"][-1]) and np.array_equal(st0[2], T[name + "_alive"][-1])
+        for mode in ("rows", "pingpong", "inplace", "sync_each", "mixed"):
+            rows, mk, na, st = run(mode)
+            if mode == "mixed":
+                f8 = np.arange(nrec) % 3 == 0
+                f4 = np.arange(nrec) % 3 == 2
+                assert np.array_equal(rows[f8], want_yx[f8]), mode
+                assert np.array_equal(rows[f4], want_yx[f4].astype(np.float32).astype(np.float64)), mode
+            else:
+                assert np.array_equal(rows, want_yx), mode
+            assert np.array_equal(mk, want_mk) and np.array_equal(na, T[name + "_nalive"]), mode
+            for a, b in zip(st, st0):
+                assert np.array_equal(a, b), mode                   # positions of discontinued buoys included
 
 
 def test_track_host_call_and_pipeline(torch, gold_track):
@@ -180,7 +249,7 @@ def test_file_dtype_rows_are_the_f4_cast_of_the_f8_rows(torch, gold_track):
             eng.track_record_host(0, T["U"][0], T["V"][0], T["IC"][0], yx, ll8, mk)
         pos, cell, alive = eng.get_state()
         assert np.array_equal(cell, T["uv1_jiT"][-1]) and np.array_equal(alive, T["uv1_alive"][-1])
-    for variant, chunk in ((0, None), (1, None), (3, None), (4, None), (0, 7)):
+    for variant, chunk in ((0, None), (1, None), (3, None), (4, None), (5, None), (0, 7)):
         with engine_for(g) as eng:
             eng.set_kernel_variant(variant)
             eng.set_buoys(T["pos0"], T["jiT0"])
@@ -389,7 +458,7 @@ def test_orientation_filter_fallbacks(torch, corc, gold_track, case):
     assert ref["ncross"] > 100
     dev = torch.device("cuda", 0)
     nP = pos0.shape[0]
-    for variant in (0, 3, 4):
+    for variant in (0, 3, 4, 5):
         with engine_for(g) as eng:
             eng.set_kernel_variant(variant)
             eng.set_buoys(pos0, T["jiT0"])
@@ -426,10 +495,12 @@ def test_large_cloud_tuned_vs_v1_vs_oracle(torch, corc, preset, n, nrec, scale):
     ref = corc.track(g, U, V, IC, pos0, cell0.astype(np.int64), history=False)
     assert ref["ncross"] > 0.02 * ik.size * nrec and ref["alive"].sum() < ik.size
     dev = torch.device("cuda", 0)
-    for variant in (0, 1, 3, 4):
+    pos_end = None
+    for variant, chain in ((0, False), (1, False), (3, False), (4, False), (5, False), (0, True), (5, True)):
         with engine_for(g) as eng:
             eng.set_kernel_variant(variant)
             eng.set_buoys(pos0, cell0)
+            eng.set_row_chain(chain)                                # chained: the ONE row buffer below is stepped in place
             eng.record_slots(1)
             yx = torch.empty((ik.size, 2), dtype=torch.float64, device=dev)
             ll = torch.empty((ik.size, 2), dtype=torch.float64, device=dev)
@@ -448,6 +519,11 @@ def test_large_cloud_tuned_vs_v1_vs_oracle(torch, corc, preset, n, nrec, scale):
             p, c, a = eng.get_state()
             assert np.array_equal(c, ref["jiT"]) and np.array_equal(a, ref["alive"])
             assert np.array_equal(na.cpu().numpy(), ref["nalive"])
+            if pos_end is None:                                     # the oracle's last recorded position of every buoy
+                assert ref["mask"][0].all()
+                last = ref["mask"].shape[0] - 1 - np.argmax(ref["mask"][::-1] == 1, axis=0)
+                pos_end = ref["posC"][last, np.arange(ik.size)]
+            assert np.array_equal(p, pos_end), (variant, chain)     # final positions, discontinued buoys included
 
 
 # ---- full season (BASELINE config 2) -------------------------------------------------------------------
