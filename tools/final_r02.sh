@@ -9,6 +9,7 @@ timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_ad
 python tools/ncu_summary.py $O/prof_r02_chain.ncu-rep $O/r02_chain > /dev/null 2>&1 && \
     python tools/update_traffic.py $O/r02_chain.json cfg5 "profiles/r02_chain.json (ncu --set full, chained default step, round 2)" && \
     cp profiles/ncu_traffic.json $O/ncu_traffic.json
+timeout 100 python __graft_entry__.py smoke > $O/r2c_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/r2c_smoke.log
 timeout 330 python -m pytest tests -m gpu -x -q -n 3 --durations=12 > $O/r2c_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 $O/r2c_pytest.log
 timeout 200 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $O/r2c_bench_ref.json 2> $O/r2c_bench_ref.err
 timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/r2c_bench.json 2> $O/r2c_bench.err; echo "bench rc=$?"
