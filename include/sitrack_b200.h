@@ -64,6 +64,8 @@ void st_destroy(st_ctx *ctx);
  *     per-cell frame in f32 when provably equal to the reference's tests, the reference's own tests in a second
  *     dense kernel otherwise (csrc/st_cert.cuh; builds the frames on first use; measured slower than 0 on B200
  *     because the second kernel re-reads what the first had in registers -- kept as an A/B);
+ *   5 variant 0 with the U/V pick of the common path taken from the certified cell frames of variant 4 (the four
+ *     U/V-point gathers only for the ~3 % of lanes that do not certify); bit-identical, measured 4 % slower than 0;
  *   6-12 round-1 experiments, present only in -DST_EXPERIMENTS builds (ST_EINVAL otherwise).                  */
 int  st_set_kernel_variant(st_ctx *ctx, int variant);
 
